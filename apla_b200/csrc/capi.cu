@@ -1,0 +1,114 @@
+// extern "C" surface declared in include/apla_b200.h: thin argument checks + forwarding to the kernels.
+#include "../../include/apla_b200.h"
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+using namespace apla;
+
+#define S(stream) reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" {
+
+const char* apla_last_error(void) { return get_error(); }
+int apla_version(void) { return 100; }
+
+int apla_device_check(void) {
+  int dev = 0, major = 0, minor = 0;
+  APLA_CUDA(cudaGetDevice(&dev));
+  APLA_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  APLA_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  APLA_CHECK(major == 10, "apla_b200 needs an sm_100 (B200) device, found compute capability %d.%d", major, minor);
+  return 0;
+}
+
+int apla_gemm_bias_fwd(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int M,
+                       int N, int K, apla_stream_t stream) {
+  return gemm_tn(EPI_BIAS, A, W, M, N, K, lda, ldw, out, nullptr, bias, nullptr, nullptr, ldo, S(stream), 0);
+}
+int apla_gemm_bias_gelu_fwd(const void* A, int lda, const void* W, int ldw, const float* bias, void* h, void* g,
+                            int ldo, int M, int N, int K, apla_stream_t stream) {
+  return gemm_tn(EPI_BIAS_GELU, A, W, M, N, K, lda, ldw, h, g, bias, nullptr, nullptr, ldo, S(stream), 0);
+}
+int apla_gemm_bias_ls_residual_fwd(const void* A, int lda, const void* W, int ldw, const float* bias,
+                                   const float* gamma, const float* resid, float* out, int ldo, int M, int N, int K,
+                                   apla_stream_t stream) {
+  return gemm_tn(EPI_RESID, A, W, M, N, K, lda, ldw, out, nullptr, bias, gamma, resid, ldo, S(stream), 0);
+}
+int apla_gemm_dgrad(const void* dY, int ldy, const void* Wt, int ldwt, void* dX, int ldx, int M, int K_in, int N_out,
+                    apla_stream_t stream) {
+  return gemm_tn(EPI_BIAS, dY, Wt, M, K_in, N_out, ldy, ldwt, dX, nullptr, nullptr, nullptr, nullptr, ldx, S(stream), 0);
+}
+int apla_gemm_dgrad_gelu_bwd(const void* dY, int ldy, const void* Wt, int ldwt, const void* h, void* dH, int ldh,
+                             int M, int K_in, int N_out, apla_stream_t stream) {
+  return gemm_tn(EPI_GELU_BWD, dY, Wt, M, K_in, N_out, ldy, ldwt, dH, nullptr, nullptr, nullptr, h, ldh, S(stream), 0);
+}
+int apla_proj_wgrad_gather(const void* dYsub, int ldy, const void* X, int ldx, const int32_t* rowmap, float* dW1,
+                           int ldw, int T, int D_in, int n_pad, int r, apla_stream_t stream) {
+  // dW1^T[D_in, n] = X^T[D_in, T] . dYsub[T, n]: D_in on the MMA M dimension, the (small) r on N
+  return gemm_wgrad_nt(X, dYsub, D_in, n_pad, T, ldx, ldy, dW1, ldw, rowmap, rowmap ? n_pad : r, S(stream));
+}
+int apla_colsum(const void* dY, int64_t ld, int T, int n, const int32_t* rowmap, float* db, apla_stream_t stream) {
+  return colsum(dY, ld, T, n, db, rowmap, S(stream));
+}
+
+int apla_layernorm_fwd(const float* x, int64_t ldx, const float* w, const float* b, void* y, int64_t ldy, int rows,
+                       int D, float eps, apla_stream_t stream) {
+  return layernorm_fwd(x, ldx, w, b, y, ldy, rows, D, eps, S(stream));
+}
+int apla_layernorm_bwd(const void* dy, int64_t ld_dy, const float* x, int64_t ldx, const float* w, const float* dres,
+                       int64_t ld_dres, float* dx, int64_t ld_dx, void* dxb, int64_t ld_dxb, const float* gamma,
+                       void* sub, int64_t ld_sub, const int32_t* idx, int r, int r_pad, int rows, int D, float eps,
+                       apla_stream_t stream) {
+  return layernorm_bwd(dy, ld_dy, x, ldx, w, dres, ld_dres, dx, ld_dx, dxb, ld_dxb, gamma, sub, ld_sub, idx, r, r_pad,
+                       rows, D, eps, S(stream));
+}
+int apla_gather_cols(const void* dy, int64_t ld, void* sub, int64_t ld_sub, const int32_t* idx, int r, int r_pad,
+                     int rows, apla_stream_t stream) {
+  return gather_cols(dy, ld, sub, ld_sub, idx, r, r_pad, rows, S(stream));
+}
+
+int apla_attn_fwd(const void* qkv, void* out, float* lse, const int32_t* cu_seqlens, int num_seqs, int max_seqlen,
+                  int H, float scale, apla_stream_t stream) {
+  return attn_fwd(qkv, out, lse, cu_seqlens, num_seqs, max_seqlen, H, scale, S(stream));
+}
+int apla_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
+                  const int32_t* cu_seqlens, int num_seqs, int max_seqlen, int total_tokens, int H, float scale,
+                  apla_stream_t stream) {
+  return attn_bwd(qkv, out, dout, lse, delta, dqkv, cu_seqlens, num_seqs, max_seqlen, total_tokens, H, scale, S(stream));
+}
+
+int apla_patchify(const float* images, void* patches, int B, int Simg, int patch, int kpad, apla_stream_t stream) {
+  return patchify(images, patches, B, Simg, patch, kpad, S(stream));
+}
+int apla_assemble_tokens(const void* patch, const float* cls, const float* pos, float* x, int B, int P, int D,
+                         apla_stream_t stream) {
+  return assemble_tokens(patch, cls, pos, x, B, P, D, S(stream));
+}
+int apla_head_fwd(const void* xn, const float* W, const float* bias, float* logits, int B, int D, int C,
+                  apla_stream_t stream) {
+  return head_fwd(xn, W, bias, logits, B, D, C, S(stream));
+}
+int apla_cross_entropy(const float* logits, const int64_t* labels, float* dlogits, float* loss, int B, int C,
+                       float grad_scale, float loss_scale, apla_stream_t stream) {
+  return cross_entropy(logits, labels, dlogits, loss, B, C, grad_scale, loss_scale, S(stream));
+}
+int apla_head_bwd(const float* dlogits, const void* xn, const float* W, float* dW, float* db, void* dxn, int B, int D,
+                  int C, apla_stream_t stream) {
+  return head_bwd(dlogits, xn, W, dW, db, dxn, B, D, C, S(stream));
+}
+
+int apla_grad_sumsq(const float* g, int64_t n, float scale, float* out, apla_stream_t stream) {
+  return grad_sumsq(g, n, scale, out, S(stream));
+}
+int apla_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t n_decay, const float* sumsq,
+                    float gscale, float max_norm, float lr, float wd, float beta1, float beta2, float eps, int step,
+                    apla_stream_t stream) {
+  return adamw_step(p, g, m, v, n, n_decay, sumsq, gscale, max_norm, lr, wd, beta1, beta2, eps, step, S(stream));
+}
+int apla_proj_refresh(const float* w1, const float* b1, const int32_t* idx, void* wfull, void* wfullT, float* bfull,
+                      int L, int r, int D, int64_t w1_block_stride, int64_t b1_block_stride, apla_stream_t stream) {
+  return proj_refresh(w1, b1, idx, wfull, wfullT, bfull, L, r, D, w1_block_stride, b1_block_stride, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,219 @@
+// Step tail: classifier head (Classifier.fc, src/defaults/models.py:87), CrossEntropyLoss(mean)
+// (src/defaults/wrappers.py:314), and the optimiser tail of Trainer.global_step (src/defaults/trainer.py:133-138):
+// clip_grad_norm_(1.0) + AdamW over ONE contiguous fp32 arena of all trainable tensors, followed by the refresh of
+// the bf16 working copies of the projection (trainable rows scattered back to their index positions,
+// src/apla/appla_attn.py:64-79).  All tiny next to the block GEMMs; written for few launches, not peak rates.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace apla {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// logits[b,c] = sum_d xn[b,d] * W[c,d] + bias[c]   (xn bf16 = LayerNorm output of the CLS token)
+__global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ xn, const float* __restrict__ W,
+                                const float* __restrict__ bias, float* __restrict__ logits, int B, int D, int C) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= B * C) return;
+  const int b = gw / C, c = gw % C;
+  float acc = 0.f;
+  for (int d = lane; d < D; d += 32) acc += __bfloat162float(xn[size_t(b) * D + d]) * __ldg(W + size_t(c) * D + d);
+  acc = warp_sum(acc);
+  // autocast hands bf16 logits to the loss; keep that rounding so the loss matches the reference's bf16 path
+  if (lane == 0) logits[gw] = acc + bias[c];
+}
+
+// per row: loss_b = logsumexp - logit[label]; dlogits = (softmax - onehot) * grad_scale; loss += loss_b * loss_scale
+__global__ void ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
+                          float* __restrict__ dlogits, float* __restrict__ loss, int C, float grad_scale,
+                          float loss_scale) {
+  const int b = blockIdx.x;
+  const float* lr = logits + size_t(b) * C;
+  __shared__ float red[32];
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, lr[c]);
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < (blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s += expf(lr[c] - mx);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) s += red[i];
+  const float lse = mx + logf(s);
+  const int y = (int)labels[b];
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    dlogits[size_t(b) * C + c] = (expf(lr[c] - lse) - (c == y ? 1.f : 0.f)) * grad_scale;
+  if (threadIdx.x == 0) atomicAdd(loss, (lse - lr[y]) * loss_scale);
+}
+
+// dW[c,d] = sum_b dlogits[b,c] * xn[b,d] ; db[c] = sum_b dlogits[b,c]
+__global__ void head_wgrad_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ xn,
+                                  float* __restrict__ dW, float* __restrict__ db, int B, int D, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * D) return;
+  const int c = i / D, d = i % D;
+  float acc = 0.f, accb = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float g = __ldg(dlogits + size_t(b) * C + c);
+    acc += g * __bfloat162float(xn[size_t(b) * D + d]);
+    accb += g;
+  }
+  dW[i] = acc;
+  if (d == 0) db[c] = accb;
+}
+
+// dxn[b,d] = sum_c dlogits[b,c] * W[c,d]  -> bf16 (gradient w.r.t. the final LayerNorm output)
+__global__ void head_dgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ W,
+                                  __nv_bfloat16* __restrict__ dxn, int B, int D, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * D) return;
+  const int b = i / D, d = i % D;
+  float acc = 0.f;
+  for (int c = 0; c < C; ++c) acc += __ldg(dlogits + size_t(b) * C + c) * __ldg(W + size_t(c) * D + d);
+  dxn[i] = __float2bfloat16_rn(acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// optimiser tail over the arena
+// ------------------------------------------------------------------------------------------------
+__global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float scale, float* __restrict__ out) {
+  float acc = 0.f;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const float v = g[i] * scale;
+    acc += v * v;
+  }
+  acc = warp_sum(acc);
+  __shared__ float red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(out, v);
+  }
+}
+
+// torch.optim.AdamW semantics (decoupled decay first, then bias-corrected update), gradients pre-scaled by
+// `gscale` (1/world for the data-parallel mean) and by the clip coefficient min(1, max_norm/(norm+1e-6)).
+// Elements [0, n_decay) get weight decay (2-D tensors), the rest do not (biases; wrappers.py:205-221).
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, int64_t n, int64_t n_decay, const float* __restrict__ sumsq,
+                             float gscale, float max_norm, float lr, float wd, float b1, float b2, float eps, float bc1,
+                             float bc2_sqrt) {
+  float coef = gscale;
+  if (max_norm > 0.f) {
+    const float norm = sqrtf(*sumsq);
+    coef *= fminf(1.f, max_norm / (norm + 1e-6f));
+  }
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * coef;
+    float pi = p[i];
+    if (i < n_decay) pi *= (1.f - lr * wd);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+// scatter the trainable projection rows back into the dense bf16 working copies:
+//   Wfull[l][idx[l][j], :] = bf16(W1[l][j, :]);  WfullT[l][:, idx[l][j]] = same;  bfull[l][idx[l][j]] = b1[l][j]
+__global__ void proj_refresh_kernel(const float* __restrict__ w1, const float* __restrict__ b1,
+                                    const int* __restrict__ idx, __nv_bfloat16* __restrict__ wfull,
+                                    __nv_bfloat16* __restrict__ wfullT, float* __restrict__ bfull, int L, int r, int D,
+                                    int64_t w1_block_stride, int64_t b1_block_stride) {
+  const int l = blockIdx.y, j = blockIdx.x;
+  const int row = idx[size_t(l) * r + j];
+  const float* src = w1 + l * w1_block_stride + size_t(j) * D;
+  __nv_bfloat16* wf = wfull + size_t(l) * D * D;
+  __nv_bfloat16* wt = wfullT + size_t(l) * D * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const __nv_bfloat16 v = __float2bfloat16_rn(src[d]);
+    wf[size_t(row) * D + d] = v;
+    wt[size_t(d) * D + row] = v;
+  }
+  if (threadIdx.x == 0) bfull[size_t(l) * D + row] = b1[l * b1_block_stride + j];
+}
+
+}  // namespace
+
+int head_fwd(const void* xn, const float* W, const float* bias, float* logits, int B, int D, int C, cudaStream_t s) {
+  APLA_CHECK(B > 0 && D > 0 && C > 0, "head_fwd: empty");
+  const int64_t threads = int64_t(B) * C * 32;
+  head_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(xn), W, bias,
+                                                                    logits, B, D, C);
+  APLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int cross_entropy(const float* logits, const int64_t* labels, float* dlogits, float* loss, int B, int C, float grad_scale,
+                  float loss_scale, cudaStream_t s) {
+  APLA_CHECK(B > 0 && C > 0, "cross_entropy: empty");
+  ce_kernel<<<B, 256, 0, s>>>(logits, labels, dlogits, loss, C, grad_scale, loss_scale);
+  APLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int head_bwd(const float* dlogits, const void* xn, const float* W, float* dW, float* db, void* dxn, int B, int D, int C,
+             cudaStream_t s) {
+  APLA_CHECK(B > 0 && D > 0 && C > 0, "head_bwd: empty");
+  head_wgrad_kernel<<<cdiv(C * D, 256), 256, 0, s>>>(dlogits, reinterpret_cast<const __nv_bfloat16*>(xn), dW, db, B, D, C);
+  APLA_CUDA(cudaGetLastError());
+  head_dgrad_kernel<<<cdiv(B * D, 256), 256, 0, s>>>(dlogits, W, reinterpret_cast<__nv_bfloat16*>(dxn), B, D, C);
+  APLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int grad_sumsq(const float* g, int64_t n, float scale, float* out, cudaStream_t s) {
+  APLA_CHECK(n > 0, "grad_sumsq: empty");
+  APLA_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
+  const int grid = (int)((n + 1023) / 1024 < 592 ? (n + 1023) / 1024 : 592);
+  sumsq_kernel<<<grid, 256, 0, s>>>(g, n, scale, out);
+  APLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int adamw_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t n_decay, const float* sumsq,
+               float gscale, float max_norm, float lr, float wd, float b1, float b2, float eps, int step,
+               cudaStream_t s) {
+  APLA_CHECK(n > 0 && step >= 1, "adamw_step: empty arena or step < 1");
+  const double bc1 = 1.0 - pow((double)b1, step);
+  const double bc2 = 1.0 - pow((double)b2, step);
+  const int grid = (int)((n + 1023) / 1024 < 1184 ? (n + 1023) / 1024 : 1184);
+  adamw_kernel<<<grid, 256, 0, s>>>(p, g, m, v, n, n_decay, sumsq, gscale, max_norm, lr, wd, b1, b2, eps, (float)bc1,
+                                    (float)sqrt(bc2));
+  APLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int proj_refresh(const float* w1, const float* b1, const int* idx, void* wfull, void* wfullT, float* bfull, int L, int r,
+                 int D, int64_t w1_block_stride, int64_t b1_block_stride, cudaStream_t s) {
+  APLA_CHECK(L > 0 && r > 0 && D > 0, "proj_refresh: empty");
+  proj_refresh_kernel<<<dim3(r, L), 256, 0, s>>>(w1, b1, idx, reinterpret_cast<__nv_bfloat16*>(wfull),
+                                                 reinterpret_cast<__nv_bfloat16*>(wfullT), bfull, L, r, D,
+                                                 w1_block_stride, b1_block_stride);
+  APLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace apla

@@ -1,0 +1,49 @@
+// Internal (C++) declarations of the kernel launchers; the C ABI in capi.cu and the step engine call these.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace apla {
+
+enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_RESID = 2, EPI_GELU_BWD = 3, EPI_F32_T = 4 };
+
+// gemm.cu
+int gemm_tn(int epi, const void* A, const void* B, int M, int N, int K, int lda, int ldb, void* out, void* out2,
+            const float* bias, const float* gamma, const void* aux, int ldo, cudaStream_t stream, int bn_override);
+int gemm_wgrad_nt(const void* A, const void* B, int M, int N, int K, int lda, int ldb, float* dW, int ldw,
+                  const int* rowmap, int n_valid, cudaStream_t stream);
+
+// attention.cu
+int attn_fwd(const void* qkv, void* out, float* lse, const int* cu_seqlens, int num_seqs, int max_seqlen, int H,
+             float scale, cudaStream_t stream);
+int attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
+             const int* cu_seqlens, int num_seqs, int max_seqlen, int total_tokens, int H, float scale,
+             cudaStream_t stream);
+
+// rowwise.cu
+int layernorm_fwd(const float* x, int64_t ldx, const float* w, const float* b, void* y, int64_t ldy, int rows, int D,
+                  float eps, cudaStream_t stream);
+int layernorm_bwd(const void* dy, int64_t ld_dy, const float* x, int64_t ldx, const float* w, const float* dres,
+                  int64_t ld_dres, float* dx, int64_t ld_dx, void* dxb, int64_t ld_dxb, const float* gamma, void* sub,
+                  int64_t ld_sub, const int* idx, int r, int r_pad, int rows, int D, float eps, cudaStream_t stream);
+int gather_cols(const void* dy, int64_t ld, void* sub, int64_t ld_sub, const int* idx, int r, int r_pad, int rows,
+                cudaStream_t stream);
+int colsum(const void* a, int64_t ld, int rows, int n, float* out, const int* rowmap, cudaStream_t stream);
+int patchify(const float* img, void* out, int B, int S, int p, int kpad, cudaStream_t stream);
+int assemble_tokens(const void* patch, const float* cls, const float* pos, float* x, int B, int P, int D,
+                    cudaStream_t stream);
+
+// head_optim.cu
+int head_fwd(const void* xn, const float* W, const float* bias, float* logits, int B, int D, int C, cudaStream_t s);
+int cross_entropy(const float* logits, const int64_t* labels, float* dlogits, float* loss, int B, int C,
+                  float grad_scale, float loss_scale, cudaStream_t s);
+int head_bwd(const float* dlogits, const void* xn, const float* W, float* dW, float* db, void* dxn, int B, int D, int C,
+             cudaStream_t s);
+int grad_sumsq(const float* g, int64_t n, float scale, float* out, cudaStream_t s);
+int adamw_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t n_decay, const float* sumsq,
+               float gscale, float max_norm, float lr, float wd, float b1, float b2, float eps, int step,
+               cudaStream_t s);
+int proj_refresh(const float* w1, const float* b1, const int* idx, void* wfull, void* wfullT, float* bfull, int L,
+                 int r, int D, int64_t w1_block_stride, int64_t b1_block_stride, cudaStream_t s);
+
+}  // namespace apla

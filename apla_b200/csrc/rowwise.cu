@@ -1,0 +1,296 @@
+// HBM-bound row kernels of the ViT block: LayerNorm forward / backward with the residual-gradient add,
+// the bf16 (LayerScale-scaled) gradient copy and the APLA column gather fused in; patch extraction; token
+// assembly (cls + pos-embed).  One warp per row, 128-bit loads/stores, row kept in registers.
+// Reference ops replaced: nn.LayerNorm(eps=1e-6) src/utils/transformers/vit.py:519,536,554,571 and :280,:285;
+// LayerScale backward vit.py:243-244; scatter_ backward (= gather) src/apla/appla_attn.py:70-79;
+// PatchEmbed / cls / pos add vit.py:304-307, :389-396.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace apla {
+
+namespace {
+
+constexpr int kMaxV4 = 8;  // D <= 1024 : up to 8 float4 per lane
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward: y_bf16 = (x - mean) * rstd * w + b
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ bias,
+              __nv_bfloat16* __restrict__ y, int64_t ldy, int rows, float eps) {
+  constexpr int D = NV * 128;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = __ldcs(xr + lane + 32 * i);
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) * (1.f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + eps);
+  uint2* yr = reinterpret_cast<uint2*>(y + row * ldy);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * i);
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + lane + 32 * i);
+    yr[lane + 32 * i] = make_uint2(pack_bf16(v[i].x * rstd * ww.x + bb.x, v[i].y * rstd * ww.y + bb.y),
+                                   pack_bf16(v[i].z * rstd * ww.z + bb.z, v[i].w * rstd * ww.w + bb.w));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward (input gradient only; weight/bias are frozen), fused with
+//   dx      = dres + LN'(dy)                      -> fp32 residual-stream gradient
+//   dxb     = bf16(gamma * dx)                    -> A operand of the next dgrad GEMM (LayerScale folded in)
+//   sub[j]  = bf16(gamma[idx[j]] * dx[idx[j]])    -> compact gathered columns for the APLA weight gradient
+// mean / rstd are recomputed from x (the row is read anyway).
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld_dy, const float* __restrict__ x, int64_t ldx,
+              const float* __restrict__ w, const float* dres, int64_t ld_dres, float* dx, int64_t ld_dx,
+              __nv_bfloat16* __restrict__ dxb, int64_t ld_dxb, const float* __restrict__ gamma,
+              __nv_bfloat16* __restrict__ sub, int64_t ld_sub, const int* __restrict__ idx, int r, int r_pad, int rows,
+              float eps) {
+  constexpr int D = NV * 128;
+  extern __shared__ float srow[];  // [warps][D], only used when sub != nullptr
+  const int wib = threadIdx.x >> 5;
+  const int row = blockIdx.x * (blockDim.x >> 5) + wib;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  const uint2* dyr = reinterpret_cast<const uint2*>(dy + row * ld_dy);
+  float4 v[NV], g[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = __ldcs(xr + lane + 32 * i);
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) * (1.f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + eps);
+  float sg = 0.f, sgx = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const uint2 d = __ldcs(dyr + lane + 32 * i);
+    const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * i);
+    v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;   // xhat
+    g[i] = make_float4(bf16_lo(d.x) * ww.x, bf16_hi(d.x) * ww.y, bf16_lo(d.y) * ww.z, bf16_hi(d.y) * ww.w);
+    sg += g[i].x + g[i].y + g[i].z + g[i].w;
+    sgx += g[i].x * v[i].x + g[i].y * v[i].y + g[i].z * v[i].z + g[i].w * v[i].w;
+  }
+  const float mg = warp_sum(sg) * (1.f / D), mgx = warp_sum(sgx) * (1.f / D);
+  const float4* rr = dres ? reinterpret_cast<const float4*>(dres + row * ld_dres) : nullptr;
+  float4* outr = reinterpret_cast<float4*>(dx + row * ld_dx);
+  uint2* outb = dxb ? reinterpret_cast<uint2*>(dxb + row * ld_dxb) : nullptr;
+  float* sr = srow + wib * D;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float4 o;
+    o.x = rstd * (g[i].x - mg - v[i].x * mgx);
+    o.y = rstd * (g[i].y - mg - v[i].y * mgx);
+    o.z = rstd * (g[i].z - mg - v[i].z * mgx);
+    o.w = rstd * (g[i].w - mg - v[i].w * mgx);
+    if (rr) {
+      const float4 r4 = __ldcs(rr + lane + 32 * i);
+      o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+    }
+    outr[lane + 32 * i] = o;
+    if (outb || sub) {
+      if (gamma) {
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+        o.x *= gm.x; o.y *= gm.y; o.z *= gm.z; o.w *= gm.w;
+      }
+      if (outb) outb[lane + 32 * i] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      if (sub) reinterpret_cast<float4*>(sr)[lane + 32 * i] = o;
+    }
+  }
+  if (sub) {
+    __syncwarp();
+    __nv_bfloat16* so = sub + row * ld_sub;
+    for (int j = lane; j < r_pad; j += 32) so[j] = __float2bfloat16_rn(j < r ? sr[__ldg(idx + j)] : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// scaled fp32 -> bf16 copy with the same gather (used where no LayerNorm precedes: nothing on the C2 path,
+// kept for the module-level API where dY arrives from autograd)
+// ------------------------------------------------------------------------------------------------
+__global__ void gather_cols_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld, __nv_bfloat16* __restrict__ sub,
+                                   int64_t ld_sub, const int* __restrict__ idx, int r, int r_pad, int rows) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= int64_t(rows) * r_pad) return;
+  const int row = int(i / r_pad), j = int(i % r_pad);
+  sub[row * ld_sub + j] = j < r ? dy[row * ld + __ldg(idx + j)] : __float2bfloat16_rn(0.f);
+}
+
+// column sums of a bf16 [rows, n] matrix -> fp32 out[map(j)] (+=): bias gradient of the trainable rows
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ a, int64_t ld, int rows, int n, float* __restrict__ out,
+                              const int* __restrict__ rowmap, int rows_per_block) {
+  // block = 32 x 8 threads: x over columns, y over row slices
+  __shared__ float red[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float acc = 0.f;
+  if (col < n)
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) acc += __bfloat162float(a[r * ld + col]);
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < n) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) acc += red[k][threadIdx.x];
+    const int o = rowmap ? rowmap[col] : col;
+    if (o >= 0) atomicAdd(out + o, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// patch extraction: images fp32 [B,3,S,S] -> bf16 [B*P, kpad], k = (c, py, px)  (conv k=s=p as a GEMM)
+// ------------------------------------------------------------------------------------------------
+__global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int S, int p,
+                                int kpad) {
+  const int g = S / p;
+  const int64_t total = int64_t(B) * g * g * kpad;
+  const int kk = 3 * p * p;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int k = int(i % kpad);
+    const int64_t pr = i / kpad;
+    float v = 0.f;
+    if (k < kk) {
+      const int px = k % p, py = (k / p) % p, c = k / (p * p);
+      const int pi = int(pr % (g * g)), b = int(pr / (g * g));
+      const int gy = pi / g, gx = pi % g;
+      v = __ldg(img + ((int64_t(b) * 3 + c) * S + gy * p + py) * S + gx * p + px);
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// tokens: x[b,0,:] = cls + pos[0];  x[b,1+i,:] = patch[b*P+i,:] + pos[1+i]      (fp32 residual stream)
+__global__ void assemble_tokens_kernel(const __nv_bfloat16* __restrict__ patch, const float* __restrict__ cls,
+                                       const float* __restrict__ pos, float* __restrict__ x, int B, int P, int D) {
+  const int64_t total = int64_t(B) * (P + 1) * (D / 4);
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int d4 = int(i % (D / 4));
+    const int64_t tok = i / (D / 4);
+    const int n = int(tok % (P + 1)), b = int(tok / (P + 1));
+    float4 v = __ldg(reinterpret_cast<const float4*>(pos) + int64_t(n) * (D / 4) + d4);
+    if (n == 0) {
+      const float4 c = __ldg(reinterpret_cast<const float4*>(cls) + d4);
+      v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+    } else {
+      const uint2 pv = __ldg(reinterpret_cast<const uint2*>(patch) + (int64_t(b) * P + n - 1) * (D / 4) + d4);
+      v.x += bf16_lo(pv.x); v.y += bf16_hi(pv.x); v.z += bf16_lo(pv.y); v.w += bf16_hi(pv.y);
+    }
+    reinterpret_cast<float4*>(x)[i] = v;
+  }
+}
+
+}  // namespace
+
+#define LN_DISPATCH(NV_, CALL)            \
+  switch (NV_) {                          \
+    case 1: { constexpr int NV = 1; CALL; } break; \
+    case 2: { constexpr int NV = 2; CALL; } break; \
+    case 3: { constexpr int NV = 3; CALL; } break; \
+    case 4: { constexpr int NV = 4; CALL; } break; \
+    case 6: { constexpr int NV = 6; CALL; } break; \
+    case 8: { constexpr int NV = 8; CALL; } break; \
+    default: set_error("layernorm: unsupported width %d (supported: 128,256,384,512,768,1024)", (NV_)*128); return 1; \
+  }
+
+int layernorm_fwd(const float* x, int64_t ldx, const float* w, const float* b, void* y, int64_t ldy, int rows, int D,
+                  float eps, cudaStream_t stream) {
+  APLA_CHECK(rows > 0, "layernorm_fwd: no rows");
+  APLA_CHECK(D % 128 == 0 && D / 128 <= kMaxV4, "layernorm_fwd: D=%d must be a multiple of 128 and <= 1024", D);
+  APLA_CHECK(ldx % 4 == 0 && ldy % 4 == 0, "layernorm_fwd: leading dimensions must be multiples of 4");
+  const int grid = cdiv(rows, 8);
+  LN_DISPATCH(D / 128, (ln_fwd_kernel<NV><<<grid, 256, 0, stream>>>(x, ldx, w, b, reinterpret_cast<__nv_bfloat16*>(y),
+                                                                    ldy, rows, eps)));
+  APLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int layernorm_bwd(const void* dy, int64_t ld_dy, const float* x, int64_t ldx, const float* w, const float* dres,
+                  int64_t ld_dres, float* dx, int64_t ld_dx, void* dxb, int64_t ld_dxb, const float* gamma, void* sub,
+                  int64_t ld_sub, const int* idx, int r, int r_pad, int rows, int D, float eps, cudaStream_t stream) {
+  APLA_CHECK(rows > 0, "layernorm_bwd: no rows");
+  APLA_CHECK(D % 128 == 0 && D / 128 <= kMaxV4, "layernorm_bwd: D=%d must be a multiple of 128 and <= 1024", D);
+  APLA_CHECK(ld_dy % 4 == 0 && ldx % 4 == 0 && ld_dx % 4 == 0 && ld_dres % 4 == 0 && ld_dxb % 4 == 0,
+             "layernorm_bwd: leading dimensions must be multiples of 4");
+  APLA_CHECK(sub == nullptr || (idx != nullptr && r <= r_pad && r_pad <= ld_sub), "layernorm_bwd: bad gather arguments");
+  const int grid = cdiv(rows, 8);
+  const size_t smem = sub ? size_t(8) * D * sizeof(float) : 0;
+  LN_DISPATCH(D / 128, (ln_bwd_kernel<NV><<<grid, 256, smem, stream>>>(
+                           reinterpret_cast<const __nv_bfloat16*>(dy), ld_dy, x, ldx, w, dres, ld_dres, dx, ld_dx,
+                           reinterpret_cast<__nv_bfloat16*>(dxb), ld_dxb, gamma, reinterpret_cast<__nv_bfloat16*>(sub),
+                           ld_sub, idx, r, r_pad, rows, eps)));
+  APLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gather_cols(const void* dy, int64_t ld, void* sub, int64_t ld_sub, const int* idx, int r, int r_pad, int rows,
+                cudaStream_t stream) {
+  const int64_t total = int64_t(rows) * r_pad;
+  APLA_CHECK(total > 0, "gather_cols: empty");
+  gather_cols_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), ld, reinterpret_cast<__nv_bfloat16*>(sub), ld_sub, idx, r, r_pad, rows);
+  APLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int colsum(const void* a, int64_t ld, int rows, int n, float* out, const int* rowmap, cudaStream_t stream) {
+  APLA_CHECK(rows > 0 && n > 0, "colsum: empty");
+  const int rows_per_block = 512;
+  dim3 grid(cdiv(n, 32), cdiv(rows, rows_per_block));
+  colsum_kernel<<<grid, dim3(32, 8), 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a), ld, rows, n, out, rowmap,
+                                                  rows_per_block);
+  APLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int patchify(const float* img, void* out, int B, int S, int p, int kpad, cudaStream_t stream) {
+  APLA_CHECK(B > 0 && S % p == 0 && kpad >= 3 * p * p, "patchify: bad shape B=%d S=%d p=%d kpad=%d", B, S, p, kpad);
+  const int64_t total = int64_t(B) * (S / p) * (S / p) * kpad;
+  const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  patchify_kernel<<<grid, 256, 0, stream>>>(img, reinterpret_cast<__nv_bfloat16*>(out), B, S, p, kpad);
+  APLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int assemble_tokens(const void* patch, const float* cls, const float* pos, float* x, int B, int P, int D,
+                    cudaStream_t stream) {
+  APLA_CHECK(B > 0 && P > 0 && D % 4 == 0, "assemble_tokens: bad shape");
+  const int64_t total = int64_t(B) * (P + 1) * (D / 4);
+  const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  assemble_tokens_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(patch), cls, pos, x, B, P, D);
+  APLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace apla

@@ -1,0 +1,166 @@
+"""Tensor-level wrappers over the C ABI (include/apla_b200.h).  Device memory comes from torch tensors, all
+arithmetic happens in libapla_b200.so on torch's current stream.  Every wrapper validates dtype / device /
+contiguity and raises; nothing here falls back to PyTorch math."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from ._lib import LIB, ptr, require_device, stream
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _chk(t: torch.Tensor, dtype, name: str, dim: Optional[int] = None):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    if dim is not None and t.dim() != dim:
+        raise RuntimeError(f"{name} must be {dim}-D, got shape {tuple(t.shape)}")
+    if t.stride(-1) != 1:
+        raise RuntimeError(f"{name} must be contiguous along the last dimension")
+
+
+def _ld(t: torch.Tensor) -> int:
+    return t.stride(0) if t.dim() == 2 else t.shape[-1]
+
+
+def gemm_bias(a, w, bias=None, out=None):
+    """out[M,N] = a[M,K] @ w[N,K]^T + bias (bf16)."""
+    require_device()
+    _chk(a, BF16, "a", 2); _chk(w, BF16, "w", 2)
+    M, K = a.shape; N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=BF16)
+    LIB.call("apla_gemm_bias_fwd", ptr(a), _ld(a), ptr(w), _ld(w), ptr(bias), ptr(out), _ld(out), M, N, K, stream())
+    return out
+
+
+def gemm_bias_gelu(a, w, bias=None, h=None, g=None):
+    require_device()
+    _chk(a, BF16, "a", 2); _chk(w, BF16, "w", 2)
+    M, K = a.shape; N = w.shape[0]
+    if h is None:
+        h = torch.empty(M, N, device=a.device, dtype=BF16)
+    if g is None:
+        g = torch.empty(M, N, device=a.device, dtype=BF16)
+    assert _ld(h) == _ld(g)
+    LIB.call("apla_gemm_bias_gelu_fwd", ptr(a), _ld(a), ptr(w), _ld(w), ptr(bias), ptr(h), ptr(g), _ld(h), M, N, K,
+             stream())
+    return h, g
+
+
+def gemm_bias_ls_residual(a, w, bias, gamma, resid, out=None):
+    """out_f32 = resid_f32 + gamma * (a @ w^T + bias); out may alias resid."""
+    require_device()
+    _chk(a, BF16, "a", 2); _chk(w, BF16, "w", 2); _chk(resid, F32, "resid", 2)
+    M, K = a.shape; N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=F32)
+    assert _ld(out) == _ld(resid)
+    LIB.call("apla_gemm_bias_ls_residual_fwd", ptr(a), _ld(a), ptr(w), _ld(w), ptr(bias), ptr(gamma), ptr(resid),
+             ptr(out), _ld(out), M, N, K, stream())
+    return out
+
+
+def gemm_dgrad(dy, wt, out=None):
+    """dx[M,Kin] = dy[M,Nout] @ wt[Kin,Nout]^T with wt the pre-transposed frozen weight."""
+    require_device()
+    _chk(dy, BF16, "dy", 2); _chk(wt, BF16, "wt", 2)
+    M, Nout = dy.shape; Kin = wt.shape[0]
+    if out is None:
+        out = torch.empty(M, Kin, device=dy.device, dtype=BF16)
+    LIB.call("apla_gemm_dgrad", ptr(dy), _ld(dy), ptr(wt), _ld(wt), ptr(out), _ld(out), M, Kin, Nout, stream())
+    return out
+
+
+def gemm_dgrad_gelu_bwd(dy, wt, h, out=None):
+    require_device()
+    _chk(dy, BF16, "dy", 2); _chk(wt, BF16, "wt", 2); _chk(h, BF16, "h", 2)
+    M, Nout = dy.shape; Kin = wt.shape[0]
+    if out is None:
+        out = torch.empty(M, Kin, device=dy.device, dtype=BF16)
+    assert _ld(out) == _ld(h)
+    LIB.call("apla_gemm_dgrad_gelu_bwd", ptr(dy), _ld(dy), ptr(wt), _ld(wt), ptr(h), ptr(out), _ld(out), M, Kin, Nout,
+             stream())
+    return out
+
+
+def proj_wgrad(dysub, x, dw1, r: int, rowmap=None):
+    """dw1_f32[r, Din] += dysub[T, n_pad]^T @ x[T, Din] (dw1 zero-initialised by the caller)."""
+    require_device()
+    _chk(dysub, BF16, "dysub", 2); _chk(x, BF16, "x", 2); _chk(dw1, F32, "dw1", 2)
+    T, n_pad = dysub.shape
+    LIB.call("apla_proj_wgrad_gather", ptr(dysub), _ld(dysub), ptr(x), _ld(x), ptr(rowmap), ptr(dw1), _ld(dw1), T,
+             x.shape[1], n_pad, r, stream())
+    return dw1
+
+
+def colsum(dy, db, n: int, rowmap=None):
+    require_device()
+    _chk(dy, BF16, "dy", 2); _chk(db, F32, "db")
+    LIB.call("apla_colsum", ptr(dy), _ld(dy), dy.shape[0], n, ptr(rowmap), ptr(db), stream())
+    return db
+
+
+def layernorm_fwd(x, w, b, eps: float, out=None):
+    require_device()
+    _chk(x, F32, "x", 2)
+    rows, D = x.shape
+    if out is None:
+        out = torch.empty(rows, D, device=x.device, dtype=BF16)
+    LIB.call("apla_layernorm_fwd", ptr(x), _ld(x), ptr(w), ptr(b), ptr(out), _ld(out), rows, D, eps, stream())
+    return out
+
+
+def layernorm_bwd(dy, x, w, eps: float, dres=None, dx=None, dxb=None, gamma=None, sub=None, idx=None, r: int = 0):
+    """dx = dres + LN'(dy); optional dxb = bf16(gamma*dx); optional sub = gathered bf16 columns."""
+    require_device()
+    _chk(dy, BF16, "dy", 2); _chk(x, F32, "x", 2)
+    rows, D = x.shape
+    if dx is None:
+        dx = torch.empty(rows, D, device=x.device, dtype=F32)
+    r_pad = sub.shape[1] if sub is not None else 0
+    LIB.call("apla_layernorm_bwd", ptr(dy), _ld(dy), ptr(x), _ld(x), ptr(w), ptr(dres),
+             _ld(dres) if dres is not None else D, ptr(dx), _ld(dx), ptr(dxb), _ld(dxb) if dxb is not None else D,
+             ptr(gamma), ptr(sub), _ld(sub) if sub is not None else 0, ptr(idx), r, r_pad, rows, D, eps, stream())
+    return dx
+
+
+def gather_cols(dy, idx, r: int, r_pad: int, out=None):
+    require_device()
+    _chk(dy, BF16, "dy", 2)
+    if out is None:
+        out = torch.empty(dy.shape[0], r_pad, device=dy.device, dtype=BF16)
+    LIB.call("apla_gather_cols", ptr(dy), _ld(dy), ptr(out), _ld(out), ptr(idx), r, r_pad, dy.shape[0], stream())
+    return out
+
+
+def attn_fwd(qkv, H: int, scale: float, num_seqs: int, max_seqlen: int, cu_seqlens=None, out=None, lse=None):
+    require_device()
+    _chk(qkv, BF16, "qkv", 2)
+    T = qkv.shape[0]
+    assert qkv.shape[1] == 3 * H * 64 and qkv.is_contiguous()
+    if out is None:
+        out = torch.empty(T, H * 64, device=qkv.device, dtype=BF16)
+    if lse is None:
+        lse = torch.empty(T, H, device=qkv.device, dtype=F32)
+    LIB.call("apla_attn_fwd", ptr(qkv), ptr(out), ptr(lse), ptr(cu_seqlens), num_seqs, max_seqlen, H, scale, stream())
+    return out, lse
+
+
+def attn_bwd(qkv, out, dout, lse, H: int, scale: float, num_seqs: int, max_seqlen: int, cu_seqlens=None, dqkv=None,
+             delta=None):
+    require_device()
+    _chk(qkv, BF16, "qkv", 2); _chk(out, BF16, "out", 2); _chk(dout, BF16, "dout", 2); _chk(lse, F32, "lse", 2)
+    T = qkv.shape[0]
+    assert dout.is_contiguous() and out.is_contiguous() and qkv.is_contiguous()
+    if dqkv is None:
+        dqkv = torch.empty_like(qkv)
+    if delta is None:
+        delta = torch.empty(T, H, device=qkv.device, dtype=F32)
+    LIB.call("apla_attn_bwd", ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqkv), ptr(cu_seqlens),
+             num_seqs, max_seqlen, T, H, scale, stream())
+    return dqkv

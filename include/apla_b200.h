@@ -1,0 +1,121 @@
+/* apla_b200 -- C ABI of the B200-native APLA fine-tune step.
+ *
+ * The reference (MoeinSorkhei/APLA) is 100 % Python/PyTorch and has no FFI; every entry point below replaces a
+ * span of ATen/cuBLAS calls issued by the reference file:line cited next to it (paths relative to the reference
+ * root).  All functions:
+ *   - take raw DEVICE pointers + sizes + a cudaStream_t (passed as void*), never torch types;
+ *   - return 0 on success, non-zero on error (message via apla_last_error(), thread-local);
+ *   - never allocate, never synchronise, never take ownership;
+ *   - require an sm_100 device (apla_device_check()).
+ * Dtypes: "bf16" = __nv_bfloat16, "f32" = float.  Matrices are row-major with an explicit leading dimension
+ * (elements).  T = tokens, D = embedding dim, H = heads (head dim is 64 everywhere).
+ */
+#ifndef APLA_B200_H_
+#define APLA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* apla_stream_t; /* cudaStream_t */
+
+/* --- library ------------------------------------------------------------------------------------------- */
+const char* apla_last_error(void);
+int apla_version(void);
+/* 0 iff the current device is compute capability 10.x (B200); the product path has no other backend. */
+int apla_device_check(void);
+
+/* --- GEMMs (tcgen05 + TMA), y = x W^T with W = [out, in] like nn.Linear ----------------------------------- */
+/* out_bf16[M,N] = A_bf16[M,K] . W_bf16[N,K]^T + bias_f32[N] (bias may be NULL).
+ * Replaces nn.Linear forward of frozen layers: self.qkv(x) src/apla/appla_attn.py:53; also used for every
+ * input-gradient GEMM dX = dY . W by passing the pre-transposed weight (apla_gemm_dgrad). */
+int apla_gemm_bias_fwd(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int M,
+                       int N, int K, apla_stream_t stream);
+/* h_bf16 = A . W^T + bias ; g_bf16 = gelu_erf(h).  Mlp.fc1 + nn.GELU, src/utils/transformers/vit.py:163-164. */
+int apla_gemm_bias_gelu_fwd(const void* A, int lda, const void* W, int ldw, const float* bias, void* h, void* g,
+                            int ldo, int M, int N, int K, apla_stream_t stream);
+/* out_f32[M,N] = resid_f32[M,N] + gamma_f32[N] * (A . W^T + bias)   (gamma NULL = 1; out may alias resid).
+ * The two F.linear + two scatter_ of src/apla/appla_attn.py:64-79 (W is the full-layout projection), or Mlp.fc2
+ * vit.py:166, followed by LayerScale vit.py:243-244 and the residual add vit.py:284-285. */
+int apla_gemm_bias_ls_residual_fwd(const void* A, int lda, const void* W, int ldw, const float* bias,
+                                   const float* gamma, const float* resid, float* out, int ldo, int M, int N, int K,
+                                   apla_stream_t stream);
+/* dX_bf16[M,K_in] = dY_bf16[M,N_out] . Wt_bf16[K_in,N_out]^T : input gradient of a frozen Linear; Wt is the
+ * transposed weight ([in, out], prepared once because the weight is frozen).  No weight gradient is computed or
+ * allocated (autograd prunes it the same way for requires_grad=False). */
+int apla_gemm_dgrad(const void* dY, int ldy, const void* Wt, int ldwt, void* dX, int ldx, int M, int K_in, int N_out,
+                    apla_stream_t stream);
+/* dH_bf16 = (dY . Wt^T) * gelu_erf'(h_bf16): fc2 input gradient fused with GELU backward (vit.py:164-166). */
+int apla_gemm_dgrad_gelu_bwd(const void* dY, int ldy, const void* Wt, int ldwt, const void* h, void* dH, int ldh,
+                             int M, int K_in, int N_out, apla_stream_t stream);
+/* APLA weight gradient.  dW1_f32[r, D_in] += dYsub^T . X  where dYsub_bf16[T, n_pad] holds the r gathered
+ * output-gradient columns (n_pad = r rounded up to 64, zero padded) and X_bf16[T, D_in] is the projection input.
+ * With rowmap != NULL, dYsub is the full [T, D_out] gradient and rowmap[n] (int32, -1 = frozen) is the
+ * trainable slot of output feature n (the partial_size == dim case).  Split-K fp32 atomics: dW1 must be zeroed
+ * by the caller.  This is autograd's backward of F.linear(x, proj_weight1) + scatter_ (appla_attn.py:64,70-74). */
+int apla_proj_wgrad_gather(const void* dYsub, int ldy, const void* X, int ldx, const int32_t* rowmap, float* dW1,
+                           int ldw, int T, int D_in, int n_pad, int r, apla_stream_t stream);
+/* db_f32[map(j)] += sum_t dY_bf16[t, j]  (bias gradient of the trainable rows). */
+int apla_colsum(const void* dY, int64_t ld, int T, int n, const int32_t* rowmap, float* db, apla_stream_t stream);
+
+/* --- LayerNorm ----------------------------------------------------------------------------------------- */
+/* y_bf16 = LayerNorm(x_f32; w, b, eps).  nn.LayerNorm(eps=1e-6) vit.py:280,285,417 (factories :519-571). */
+int apla_layernorm_fwd(const float* x, int64_t ldx, const float* w, const float* b, void* y, int64_t ldy, int rows,
+                       int D, float eps, apla_stream_t stream);
+/* dx_f32 = dres_f32 + LayerNorm'(dy_bf16) (dres NULL = 0; dx may alias dres);
+ * dxb_bf16 = gamma * dx (optional); sub_bf16[t, j<r] = gamma[idx[j]] * dx[t, idx[j]], zero for r <= j < r_pad
+ * (optional): residual-gradient add + LayerScale backward + APLA column gather in one pass. */
+int apla_layernorm_bwd(const void* dy, int64_t ld_dy, const float* x, int64_t ldx, const float* w, const float* dres,
+                       int64_t ld_dres, float* dx, int64_t ld_dx, void* dxb, int64_t ld_dxb, const float* gamma,
+                       void* sub, int64_t ld_sub, const int32_t* idx, int r, int r_pad, int rows, int D, float eps,
+                       apla_stream_t stream);
+/* sub_bf16[t, j] = dy_bf16[t, idx[j]] (j < r), 0 (r <= j < r_pad). */
+int apla_gather_cols(const void* dy, int64_t ld, void* sub, int64_t ld_sub, const int32_t* idx, int r, int r_pad,
+                     int rows, apla_stream_t stream);
+
+/* --- attention ------------------------------------------------------------------------------------------ */
+/* out_bf16[T, H*64] = softmax(scale * q k^T) v per sequence and head; lse_f32[T, H] saved for backward.
+ * qkv_bf16[T, 3*H*64] laid out (3, H, 64) along the last dim (appla_attn.py:53-54).  cu_seqlens = NULL: num_seqs
+ * sequences of max_seqlen tokens (appla_attn.py:56-60); otherwise int32[num_seqs+1] packed offsets = the
+ * BlockDiagonalMask of appla_attn_mem_eff.py:37-43 / dinov2/layers/block.py:191-217. */
+int apla_attn_fwd(const void* qkv, void* out, float* lse, const int32_t* cu_seqlens, int num_seqs, int max_seqlen,
+                  int H, float scale, apla_stream_t stream);
+/* dqkv_bf16[T, 3*H*64] from dout_bf16[T, H*64]; delta_f32[T, H] is workspace. */
+int apla_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
+                  const int32_t* cu_seqlens, int num_seqs, int max_seqlen, int total_tokens, int H, float scale,
+                  apla_stream_t stream);
+
+/* --- step ends ------------------------------------------------------------------------------------------ */
+/* patches_bf16[B*P, kpad] from images_f32[B,3,S,S], k = (c, py, px): PatchEmbed conv as a GEMM, vit.py:302-306. */
+int apla_patchify(const float* images, void* patches, int B, int S, int patch, int kpad, apla_stream_t stream);
+/* x_f32[B, P+1, D] = cat(cls, patch_bf16) + pos_f32[P+1, D]   (vit.py:392-396; pos already interpolated). */
+int apla_assemble_tokens(const void* patch, const float* cls, const float* pos, float* x, int B, int P, int D,
+                         apla_stream_t stream);
+/* logits_f32[B,C] = xn_bf16[B,D] . W_f32[C,D]^T + bias   (Classifier.fc, src/defaults/models.py:87). */
+int apla_head_fwd(const void* xn, const float* W, const float* bias, float* logits, int B, int D, int C,
+                  apla_stream_t stream);
+/* *loss += loss_scale * sum_b CE_b ; dlogits = grad_scale * (softmax - onehot)   (wrappers.py:314). */
+int apla_cross_entropy(const float* logits, const int64_t* labels, float* dlogits, float* loss, int B, int C,
+                       float grad_scale, float loss_scale, apla_stream_t stream);
+/* dW_f32[C,D], db_f32[C] (overwritten) and dxn_bf16[B,D]. */
+int apla_head_bwd(const float* dlogits, const void* xn, const float* W, float* dW, float* db, void* dxn, int B, int D,
+                  int C, apla_stream_t stream);
+
+/* --- optimiser tail over one contiguous fp32 arena -------------------------------------------------------- */
+/* *out = sum (scale*g)^2 */
+int apla_grad_sumsq(const float* g, int64_t n, float scale, float* out, apla_stream_t stream);
+/* clip_grad_norm_(max_norm) (trainer.py:136) + torch.optim.AdamW step (wrappers.py:199-221): elements
+ * [0,n_decay) are decayed.  gscale pre-multiplies the gradients (1/world for the DDP mean). */
+int apla_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t n_decay, const float* sumsq,
+                    float gscale, float max_norm, float lr, float wd, float beta1, float beta2, float eps, int step,
+                    apla_stream_t stream);
+/* Scatter trainable rows into the dense bf16 projection copies (appla_attn.py:70-79 done once per update). */
+int apla_proj_refresh(const float* w1, const float* b1, const int32_t* idx, void* wfull, void* wfullT, float* bfull,
+                      int L, int r, int D, int64_t w1_block_stride, int64_t b1_block_stride, apla_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APLA_B200_H_ */

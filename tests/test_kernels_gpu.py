@@ -1,0 +1,227 @@
+"""Kernel-level parity on the B200: every C-ABI kernel against a plain PyTorch fp32 restatement of the same op
+on the same (bf16-rounded) inputs.  Tolerances are the bf16 output rounding (2^-8 relative) unless stated."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from apla_b200 import ops
+    return ops
+
+
+def rel(a, b):
+    a = a.double().flatten(); b = b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 384, 128), (1576, 1152, 384), (16448, 768, 768),
+                                   (514, 2304, 768), (2 * 257, 3072, 768), (100, 128, 3072), (257, 32, 64)])
+def test_gemm_bias(M, N, K):
+    ops = _cuda()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = bf(torch.randn(M, K, device="cuda", generator=g))
+    w = bf(torch.randn(N, K, device="cuda", generator=g) * 0.05)
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = ops.gemm_bias(a, w, bias)
+    ref = a.float() @ w.float().t() + bias
+    assert rel(out.float(), ref) < 4e-3
+    assert torch.allclose(out.float(), ref, atol=2e-2, rtol=1e-2)
+    out2 = ops.gemm_bias(a, w, None)
+    assert rel(out2.float(), a.float() @ w.float().t()) < 4e-3
+
+
+@pytest.mark.parametrize("bn", [64, 128, 256])
+def test_gemm_all_tile_widths(bn):
+    """Force each BN instantiation through the internal override (exported for tests via env)."""
+    ops = _cuda()
+    import os
+    os.environ["APLA_GEMM_BN"] = str(bn)
+    try:
+        g = torch.Generator(device="cuda").manual_seed(bn)
+        a = bf(torch.randn(1000, 512, device="cuda", generator=g))
+        w = bf(torch.randn(768, 512, device="cuda", generator=g) * 0.05)
+        out = ops.gemm_bias(a, w, None)
+        assert rel(out.float(), a.float() @ w.float().t()) < 4e-3
+    finally:
+        del os.environ["APLA_GEMM_BN"]
+
+
+def test_gemm_bias_gelu():
+    ops = _cuda()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = bf(torch.randn(777, 384, device="cuda", generator=g))
+    w = bf(torch.randn(1536, 384, device="cuda", generator=g) * 0.05)
+    bias = torch.randn(1536, device="cuda", generator=g) * 0.1
+    h, gl = ops.gemm_bias_gelu(a, w, bias)
+    href = a.float() @ w.float().t() + bias
+    assert rel(h.float(), href) < 4e-3
+    gref = torch.nn.functional.gelu(h.float())          # GELU of the stored bf16 pre-activation
+    assert rel(gl.float(), gref) < 4e-3
+
+
+def test_gemm_ls_residual_inplace():
+    ops = _cuda()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    M, N, K = 1028, 768, 3072
+    a = bf(torch.randn(M, K, device="cuda", generator=g))
+    w = bf(torch.randn(N, K, device="cuda", generator=g) * 0.02)
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    gamma = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    ref = resid + gamma * (a.float() @ w.float().t() + bias)
+    out = ops.gemm_bias_ls_residual(a, w, bias, gamma, resid)
+    assert rel(out, ref) < 1e-3
+    r2 = resid.clone()
+    ops.gemm_bias_ls_residual(a, w, bias, None, r2, out=r2)
+    assert rel(r2, resid + (a.float() @ w.float().t() + bias)) < 1e-3
+
+
+def test_gemm_dgrad_and_gelu_bwd():
+    ops = _cuda()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    M, Din, Dout = 900, 1536, 384           # fc2: in=1536, out=384
+    dy = bf(torch.randn(M, Dout, device="cuda", generator=g))
+    W = bf(torch.randn(Dout, Din, device="cuda", generator=g) * 0.05)    # [out, in]
+    wt = W.t().contiguous()                                               # [in, out]
+    dx = ops.gemm_dgrad(dy, wt)
+    ref = dy.float() @ W.float()
+    assert rel(dx.float(), ref) < 4e-3
+    h = bf(torch.randn(M, Din, device="cuda", generator=g))
+    dh = ops.gemm_dgrad_gelu_bwd(dy, wt, h)
+    hh = h.float().requires_grad_(True)
+    torch.nn.functional.gelu(hh).backward(ref)
+    assert rel(dh.float(), hh.grad) < 5e-3
+
+
+@pytest.mark.parametrize("T,D,r", [(514, 768, 8), (1576, 384, 32), (2000, 768, 128), (16448, 768, 8)])
+def test_proj_wgrad_compact(T, D, r):
+    ops = _cuda()
+    g = torch.Generator(device="cuda").manual_seed(T + r)
+    x = bf(torch.randn(T, D, device="cuda", generator=g))
+    dy = bf(torch.randn(T, D, device="cuda", generator=g))
+    idx = torch.randperm(D, device="cuda", generator=g)[:r].to(torch.int32)
+    n_pad = (r + 63) // 64 * 64
+    sub = ops.gather_cols(dy, idx, r, n_pad)
+    assert torch.equal(sub[:, :r], dy[:, idx.long()]) and float(sub[:, r:].abs().sum()) == 0.0
+    dw = torch.zeros(r, D, device="cuda")
+    ops.proj_wgrad(sub, x, dw, r)
+    ref = dy[:, idx.long()].float().t() @ x.float()
+    assert rel(dw, ref) < 1e-3
+    db = torch.zeros(r, device="cuda")
+    ops.colsum(sub, db, r)
+    assert rel(db, dy[:, idx.long()].float().sum(0)) < 1e-3
+
+
+def test_proj_wgrad_full_rowmap():
+    """partial_size == dim: full dY as the B operand, rows permuted through rowmap in the epilogue."""
+    ops = _cuda()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    T, D = 1542, 768
+    x = bf(torch.randn(T, D, device="cuda", generator=g))
+    dy = bf(torch.randn(T, D, device="cuda", generator=g))
+    perm = torch.randperm(D, device="cuda", generator=g)
+    rowmap = torch.empty(D, dtype=torch.int32, device="cuda")
+    rowmap[perm] = torch.arange(D, dtype=torch.int32, device="cuda")      # slot of output feature n
+    dw = torch.zeros(D, D, device="cuda")
+    ops.proj_wgrad(dy, x, dw, D, rowmap=rowmap)
+    ref = dy[:, perm].float().t() @ x.float()
+    assert rel(dw, ref) < 1e-3
+    db = torch.zeros(D, device="cuda")
+    ops.colsum(dy, db, D, rowmap=rowmap)
+    assert rel(db, dy[:, perm].float().sum(0)) < 1e-3
+
+
+@pytest.mark.parametrize("D", [128, 384, 768, 1024])
+def test_layernorm_fwd_bwd(D):
+    ops = _cuda()
+    g = torch.Generator(device="cuda").manual_seed(D)
+    rows, r = 1031, 16
+    x = torch.randn(rows, D, device="cuda", generator=g) * 2 + 0.5
+    w = torch.randn(D, device="cuda", generator=g)
+    b = torch.randn(D, device="cuda", generator=g)
+    y = ops.layernorm_fwd(x, w, b, 1e-6)
+    ref = torch.nn.functional.layer_norm(x, (D,), w, b, 1e-6)
+    assert rel(y.float(), ref) < 3e-3
+    dy = bf(torch.randn(rows, D, device="cuda", generator=g))
+    dres = torch.randn(rows, D, device="cuda", generator=g)
+    gamma = torch.randn(D, device="cuda", generator=g)
+    idx = torch.randperm(D, device="cuda", generator=g)[:r].to(torch.int32)
+    xx = x.clone().requires_grad_(True)
+    torch.nn.functional.layer_norm(xx, (D,), w, b, 1e-6).backward(dy.float())
+    dx_ref = dres + xx.grad
+    dxb = torch.empty(rows, D, device="cuda", dtype=torch.bfloat16)
+    sub = torch.empty(rows, 64, device="cuda", dtype=torch.bfloat16)
+    dx = ops.layernorm_bwd(dy, x, w, 1e-6, dres=dres, dxb=dxb, gamma=gamma, sub=sub, idx=idx, r=r)
+    assert rel(dx, dx_ref) < 1e-5
+    assert rel(dxb.float(), gamma * dx_ref) < 3e-3
+    assert rel(sub[:, :r].float(), (gamma * dx_ref)[:, idx.long()]) < 3e-3
+    assert float(sub[:, r:].abs().sum()) == 0.0
+    # in place on the residual gradient, no extras
+    d2 = dres.clone()
+    ops.layernorm_bwd(dy, x, w, 1e-6, dres=d2, dx=d2)
+    assert rel(d2, dx_ref) < 1e-5
+    # strided rows (CLS-only final norm): every 5th row of x
+    ys = ops.layernorm_fwd(x[::5], w, b, 1e-6)
+    assert rel(ys.float(), ref[::5]) < 3e-3
+
+
+def _attn_ref(qkv, seqlens, H, scale):
+    """fp32 restatement of appla_attn.py:53-60 per sequence, with autograd for the backward."""
+    outs = []
+    o = 0
+    D = H * 64
+    for n in seqlens:
+        t = qkv[o:o + n].reshape(n, 3, H, 64).permute(1, 2, 0, 3)
+        q, k, v = t[0], t[1], t[2]
+        a = ((q @ k.transpose(-2, -1)) * scale).softmax(-1)
+        outs.append((a @ v).transpose(0, 1).reshape(n, D))
+        o += n
+    return torch.cat(outs, 0)
+
+
+@pytest.mark.parametrize("B,N,H", [(2, 257, 12), (3, 197, 6), (1, 1370, 12), (4, 50, 16), (2, 64, 2), (5, 17, 2)])
+def test_attention_dense(B, N, H):
+    ops = _cuda()
+    g = torch.Generator(device="cuda").manual_seed(B * N + H)
+    D = H * 64
+    qkv = bf(torch.randn(B * N, 3 * D, device="cuda", generator=g))
+    scale = 64 ** -0.5
+    out, lse = ops.attn_fwd(qkv, H, scale, B, N)
+    q32 = qkv.float().requires_grad_(True)
+    ref = _attn_ref(q32, [N] * B, H, scale)
+    assert rel(out.float(), ref) < 6e-3
+    dout = bf(torch.randn(B * N, D, device="cuda", generator=g))
+    ref.backward(dout.float())
+    dqkv = ops.attn_bwd(qkv, out, dout, lse, H, scale, B, N)
+    assert rel(dqkv.float(), q32.grad) < 1e-2
+    for part, name in ((slice(0, D), "dq"), (slice(D, 2 * D), "dk"), (slice(2 * D, 3 * D), "dv")):
+        assert rel(dqkv[:, part].float(), q32.grad[:, part]) < 1.2e-2, name
+
+
+def test_attention_varlen():
+    ops = _cuda()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    H, D = 4, 256
+    seqlens = [257, 50, 257, 50, 50, 3, 130]
+    T = sum(seqlens)
+    cu = torch.tensor([0] + list(torch.tensor(seqlens).cumsum(0)), dtype=torch.int32, device="cuda")
+    qkv = bf(torch.randn(T, 3 * D, device="cuda", generator=g))
+    scale = 0.125
+    out, lse = ops.attn_fwd(qkv, H, scale, len(seqlens), max(seqlens), cu_seqlens=cu)
+    q32 = qkv.float().requires_grad_(True)
+    ref = _attn_ref(q32, seqlens, H, scale)
+    assert rel(out.float(), ref) < 6e-3
+    dout = bf(torch.randn(T, D, device="cuda", generator=g))
+    ref.backward(dout.float())
+    dqkv = ops.attn_bwd(qkv, out, dout, lse, H, scale, len(seqlens), max(seqlens), cu_seqlens=cu)
+    assert rel(dqkv.float(), q32.grad) < 1e-2
