@@ -27,7 +27,7 @@ def parse_header(path: str = HEADER) -> Dict[str, Tuple[object, List[object]]]:
     src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
     src = re.sub(r"//[^\n]*", " ", src)
     protos = {}
-    for m in re.finditer(r"(const\s+char\s*\*|int|void|apla_engine_t)\s+(apla_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"(const\s+char\s*\*|int64_t|int|void|apla_engine_t)\s+(apla_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
         ret, name, args = m.group(1), m.group(2), m.group(3)
         if ret.startswith("const"):
             restype = ctypes.c_char_p

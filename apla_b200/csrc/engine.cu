@@ -1,0 +1,317 @@
+// Step engine: the whole APLA fine-tune step (Trainer.global_step, src/defaults/trainer.py:106-138, over
+// Classifier.forward src/defaults/models.py:81-92 and Block.forward src/utils/transformers/vit.py:279-288) as ONE
+// native call sequence on one stream -- no Python between kernels, capturable in a CUDA graph.
+//
+// The engine owns no memory: the host side (apla_b200/engine.py) allocates every buffer (torch tensors), hands the
+// device pointers over by name, and keeps them alive.  Gradient flow implemented here = exactly what autograd
+// computes for the reference: input gradients everywhere a trainable tensor sits upstream, weight gradients only
+// for the APLA rows of every projection and for the classifier head; block 0's attention / qkv / proj input
+// gradients are skipped because nothing upstream of them is trainable.
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/apla_b200.h"
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace apla {
+
+struct BlockPtrs {
+  // frozen weights (bf16 working copies, [out,in] and pre-transposed [in,out]) and fp32 vectors
+  const void *wqkv = nullptr, *wqkvT = nullptr, *wfc1 = nullptr, *wfc1T = nullptr, *wfc2 = nullptr, *wfc2T = nullptr;
+  void *wproj = nullptr, *wprojT = nullptr;  // dense projection copies, refreshed after every update
+  const float *bqkv = nullptr, *bfc1 = nullptr, *bfc2 = nullptr, *ln1w = nullptr, *ln1b = nullptr, *ln2w = nullptr,
+              *ln2b = nullptr, *g1 = nullptr, *g2 = nullptr;
+  float* bproj = nullptr;
+  // saved activations
+  void *qkv = nullptr, *ao = nullptr, *hpre = nullptr;
+  float* lse = nullptr;
+};
+
+struct Engine {
+  // shape
+  int B = 0, N = 0, D = 0, H = 0, L = 0, hidden = 0, C = 0, P = 0, patch = 0, img = 0, kpad = 0;
+  int r = 0, r_pad = 0, full_rows = 0;  // full_rows: partial_size == dim handled through rowmap on the dense dY
+  float eps = 1e-6f, scale = 0.125f;
+  std::vector<BlockPtrs> blk;
+  std::map<std::string, void*> g;  // global buffers by name
+  std::string err;
+  int T() const { return B * N; }
+  template <class Tp>
+  Tp* get(const char* name) {
+    auto it = g.find(name);
+    return it == g.end() ? nullptr : reinterpret_cast<Tp*>(it->second);
+  }
+};
+
+static const char* kGlobalNames[] = {
+    // inputs / embedding
+    "patches", "wpe", "bpe", "pe_out", "cls", "pos",
+    // residual stream checkpoints xs[0..2L] as one [2L+1, T, D] fp32 buffer
+    "xs",
+    // transients
+    "ln_out", "gelu_out", "dx", "dxb", "dsub", "dO", "dqkv", "delta",
+    // final norm + head
+    "lnfw", "lnfb", "cls_ln", "logits", "dlogits", "loss", "dcls",
+    // trainable arena (params / grads / adam moments), index tables, scratch
+    "params", "grads", "exp_avg", "exp_avg_sq", "idx", "rowmap", "sumsq",
+};
+
+static int check_ready(Engine* e) {
+  for (const char* n : kGlobalNames) {
+    if (std::string(n) == "rowmap" && !e->full_rows) continue;
+    if (std::string(n) == "dsub" && e->full_rows) continue;
+    APLA_CHECK(e->g.count(n) && e->g[n] != nullptr, "engine: buffer '%s' was not set", n);
+  }
+  for (int l = 0; l < e->L; ++l) {
+    const BlockPtrs& b = e->blk[l];
+    APLA_CHECK(b.wqkv && b.wqkvT && b.wfc1 && b.wfc1T && b.wfc2 && b.wfc2T && b.wproj && b.wprojT && b.bproj &&
+                   b.bfc1 && b.bfc2 && b.ln1w && b.ln1b && b.ln2w && b.ln2b && b.qkv && b.ao && b.hpre && b.lse,
+               "engine: block %d has unset pointers", l);
+  }
+  return 0;
+}
+
+// arena layout: [W1 (L x r x D) | fc.weight (C x D) | b1 (L x r) | fc.bias (C)]
+struct Arena {
+  int64_t w1, fcw, b1, fcb, n, n_decay;
+};
+static Arena arena_of(const Engine* e) {
+  Arena a;
+  a.w1 = 0;
+  a.fcw = int64_t(e->L) * e->r * e->D;
+  a.b1 = a.fcw + int64_t(e->C) * e->D;
+  a.fcb = a.b1 + int64_t(e->L) * e->r;
+  a.n = a.fcb + e->C;
+  a.n_decay = a.b1;
+  return a;
+}
+
+static int engine_forward(Engine* e, const float* images, const int64_t* labels, float loss_scale, float grad_scale,
+                          cudaStream_t s) {
+  if (int rc = check_ready(e)) return rc;
+  const int T = e->T(), D = e->D, B = e->B, N = e->N, L = e->L, Hd = e->hidden;
+  const size_t TD = size_t(T) * D;
+  float* xs = e->get<float>("xs");
+  void* ln_out = e->get<void>("ln_out");
+  void* gelu_out = e->get<void>("gelu_out");
+  const Arena ar = arena_of(e);
+  float* params = e->get<float>("params");
+
+  // ---- patch embedding + cls + pos (vit.py:389-396) ----
+  if (int rc = patchify(images, e->get<void>("patches"), B, e->img, e->patch, e->kpad, s)) return rc;
+  if (int rc = gemm_tn(EPI_BIAS, e->get<void>("patches"), e->get<void>("wpe"), B * e->P, D, e->kpad, e->kpad, e->kpad,
+                       e->get<void>("pe_out"), nullptr, e->get<float>("bpe"), nullptr, nullptr, D, s, 0))
+    return rc;
+  if (int rc = assemble_tokens(e->get<void>("pe_out"), e->get<float>("cls"), e->get<float>("pos"), xs, B, e->P, D, s))
+    return rc;
+
+  // ---- blocks (vit.py:279-288) ----
+  for (int l = 0; l < L; ++l) {
+    const BlockPtrs& b = e->blk[l];
+    float* x_in = xs + size_t(2 * l) * TD;
+    float* x_mid = xs + size_t(2 * l + 1) * TD;
+    float* x_out = xs + size_t(2 * l + 2) * TD;
+    if (int rc = layernorm_fwd(x_in, D, b.ln1w, b.ln1b, ln_out, D, T, D, e->eps, s)) return rc;
+    if (int rc = gemm_tn(EPI_BIAS, ln_out, b.wqkv, T, 3 * D, D, D, D, b.qkv, nullptr, b.bqkv, nullptr, nullptr, 3 * D, s, 0))
+      return rc;
+    if (int rc = attn_fwd(b.qkv, b.ao, b.lse, nullptr, B, N, e->H, e->scale, s)) return rc;
+    if (int rc = gemm_tn(EPI_RESID, b.ao, b.wproj, T, D, D, D, D, x_mid, nullptr, b.bproj, b.g1, x_in, D, s, 0)) return rc;
+    if (int rc = layernorm_fwd(x_mid, D, b.ln2w, b.ln2b, ln_out, D, T, D, e->eps, s)) return rc;
+    if (int rc = gemm_tn(EPI_BIAS_GELU, ln_out, b.wfc1, T, Hd, D, D, D, b.hpre, gelu_out, b.bfc1, nullptr, nullptr, Hd, s, 0))
+      return rc;
+    if (int rc = gemm_tn(EPI_RESID, gelu_out, b.wfc2, T, D, Hd, Hd, Hd, x_out, nullptr, b.bfc2, b.g2, x_mid, D, s, 0))
+      return rc;
+  }
+
+  // ---- final norm on the CLS rows only (vit.py:417-419), head, loss ----
+  const float* x_fin = xs + size_t(2 * L) * TD;
+  if (int rc = layernorm_fwd(x_fin, int64_t(N) * D, e->get<float>("lnfw"), e->get<float>("lnfb"), e->get<void>("cls_ln"),
+                             D, B, D, e->eps, s))
+    return rc;
+  if (int rc = head_fwd(e->get<void>("cls_ln"), params + ar.fcw, params + ar.fcb, e->get<float>("logits"), B, D, e->C, s))
+    return rc;
+  if (labels) {
+    APLA_CUDA(cudaMemsetAsync(e->get<float>("loss"), 0, sizeof(float), s));
+    if (int rc = cross_entropy(e->get<float>("logits"), labels, e->get<float>("dlogits"), e->get<float>("loss"), B, e->C,
+                               grad_scale, loss_scale, s))
+      return rc;
+  }
+  return 0;
+}
+
+static int engine_backward(Engine* e, int l_from, int l_to, cudaStream_t s) {
+  if (int rc = check_ready(e)) return rc;
+  const int T = e->T(), D = e->D, B = e->B, N = e->N, L = e->L, Hd = e->hidden, r = e->r;
+  const size_t TD = size_t(T) * D;
+  float* xs = e->get<float>("xs");
+  void* dln = e->get<void>("ln_out");      // reused: gradient w.r.t. a LayerNorm output
+  void* dH = e->get<void>("gelu_out");     // reused: gradient w.r.t. the fc1 pre-activation
+  float* dx = e->get<float>("dx");
+  void* dxb = e->get<void>("dxb");
+  void* dsub = e->full_rows ? nullptr : e->get<void>("dsub");
+  const int* idx = e->get<int>("idx");
+  const int* rowmap = e->full_rows ? e->get<int>("rowmap") : nullptr;
+  const Arena ar = arena_of(e);
+  float* params = e->get<float>("params");
+  float* grads = e->get<float>("grads");
+
+  APLA_CHECK(0 <= l_to && l_to <= l_from && l_from < L, "engine_backward: bad block range [%d..%d]", l_from, l_to);
+  if (l_from == L - 1) {
+  APLA_CUDA(cudaMemsetAsync(grads, 0, size_t(ar.n) * sizeof(float), s));
+  // head: dW, db, and the gradient of the normalised CLS token
+  if (int rc = head_bwd(e->get<float>("dlogits"), e->get<void>("cls_ln"), params + ar.fcw, grads + ar.fcw, grads + ar.fcb,
+                        e->get<void>("dcls"), B, D, e->C, s))
+    return rc;
+  // final norm backward: only CLS rows carry gradient; everything else in dx / dxb is zero
+  APLA_CUDA(cudaMemsetAsync(dx, 0, TD * sizeof(float), s));
+  APLA_CUDA(cudaMemsetAsync(dxb, 0, TD * 2, s));
+  if (int rc = layernorm_bwd(e->get<void>("dcls"), D, xs + size_t(2 * L) * TD, int64_t(N) * D, e->get<float>("lnfw"),
+                             nullptr, 0, dx, int64_t(N) * D, dxb, int64_t(N) * D, e->blk[L - 1].g2, nullptr, 0, nullptr, 0,
+                             0, B, D, e->eps, s))
+    return rc;
+  }
+
+  for (int l = l_from; l >= l_to; --l) {
+    const BlockPtrs& b = e->blk[l];
+    const float* x_in = xs + size_t(2 * l) * TD;
+    const float* x_mid = xs + size_t(2 * l + 1) * TD;
+    // MLP branch: dxb holds bf16(gamma2 * dx_out)
+    if (int rc = gemm_tn(EPI_GELU_BWD, dxb, b.wfc2T, T, Hd, D, D, D, dH, nullptr, nullptr, nullptr, b.hpre, Hd, s, 0))
+      return rc;
+    if (int rc = gemm_tn(EPI_BIAS, dH, b.wfc1T, T, D, Hd, Hd, Hd, dln, nullptr, nullptr, nullptr, nullptr, D, s, 0))
+      return rc;
+    // dx_mid = dx_out + LN2'(dln); dxb = bf16(gamma1 * dx_mid); dsub = its APLA columns
+    if (int rc = layernorm_bwd(dln, D, x_mid, D, b.ln2w, dx, D, dx, D, dxb, D, b.g1, dsub, e->r_pad,
+                               idx + size_t(l) * r, r, e->r_pad, T, D, e->eps, s))
+      return rc;
+    // APLA weight gradient: only the trainable rows of the projection (appla_attn.py:64,70-74)
+    float* dW1 = grads + ar.w1 + size_t(l) * r * D;
+    float* db1 = grads + ar.b1 + size_t(l) * r;
+    if (e->full_rows) {
+      if (int rc = gemm_wgrad_nt(b.ao, dxb, D, D, T, D, D, dW1, D, rowmap + size_t(l) * D, D, s)) return rc;
+      if (int rc = colsum(dxb, D, T, D, db1, rowmap + size_t(l) * D, s)) return rc;
+    } else {
+      if (int rc = gemm_wgrad_nt(b.ao, dsub, D, e->r_pad, T, D, e->r_pad, dW1, D, nullptr, r, s)) return rc;
+      if (int rc = colsum(dsub, e->r_pad, T, r, db1, nullptr, s)) return rc;
+    }
+    if (l == 0) break;  // nothing trainable upstream of block 0's attention
+    void* dO = e->get<void>("dO");
+    if (int rc = gemm_tn(EPI_BIAS, dxb, b.wprojT, T, D, D, D, D, dO, nullptr, nullptr, nullptr, nullptr, D, s, 0)) return rc;
+    if (int rc = attn_bwd(b.qkv, b.ao, dO, b.lse, e->get<float>("delta"), e->get<void>("dqkv"), nullptr, B, N, T, e->H,
+                          e->scale, s))
+      return rc;
+    if (int rc = gemm_tn(EPI_BIAS, e->get<void>("dqkv"), b.wqkvT, T, D, 3 * D, 3 * D, 3 * D, dln, nullptr, nullptr, nullptr,
+                         nullptr, D, s, 0))
+      return rc;
+    // dx_in = dx_mid + LN1'(dln); dxb = bf16(gamma2[l-1] * dx_in) feeds block l-1's MLP branch
+    if (int rc = layernorm_bwd(dln, D, x_in, D, b.ln1w, dx, D, dx, D, dxb, D, e->blk[l - 1].g2, nullptr, 0, nullptr, 0, 0,
+                               T, D, e->eps, s))
+      return rc;
+  }
+  return 0;
+}
+
+static int engine_optim(Engine* e, float gscale, float max_norm, float lr, float wd, float b1, float b2, float eps,
+                        int step, cudaStream_t s) {
+  if (int rc = check_ready(e)) return rc;
+  const Arena ar = arena_of(e);
+  float* params = e->get<float>("params");
+  float* grads = e->get<float>("grads");
+  float* sumsq = e->get<float>("sumsq");
+  if (int rc = grad_sumsq(grads, ar.n, gscale, sumsq, s)) return rc;
+  if (int rc = adamw_step(params, grads, e->get<float>("exp_avg"), e->get<float>("exp_avg_sq"), ar.n, ar.n_decay, sumsq,
+                          gscale, max_norm, lr, wd, b1, b2, eps, step, s))
+    return rc;
+  // refresh the dense bf16 projection copies from the updated fp32 rows
+  const int L = e->L, r = e->r, D = e->D;
+  // blocks' dense copies are separate allocations: refresh one block per launch row via per-block pointers
+  for (int l = 0; l < L; ++l) {
+    if (int rc = proj_refresh(params + ar.w1 + size_t(l) * r * D, params + ar.b1 + size_t(l) * r,
+                              e->get<int>("idx") + size_t(l) * r, e->blk[l].wproj, e->blk[l].wprojT, e->blk[l].bproj, 1, r,
+                              D, 0, 0, s))
+      return rc;
+  }
+  return 0;
+}
+
+}  // namespace apla
+
+using namespace apla;
+
+extern "C" {
+
+apla_engine_t apla_engine_create(int B, int N, int D, int H, int L, int hidden, int C, int patch, int img, int kpad, int r,
+                                 int r_pad, int full_rows, float eps, float scale) {
+  if (B <= 0 || N <= 1 || D % 128 != 0 || H * 64 != D || L <= 0 || hidden % 32 != 0 || C <= 0 || r <= 0 || r > D ||
+      img % patch != 0 || (img / patch) * (img / patch) + 1 != N || kpad % 8 != 0 || kpad < 3 * patch * patch ||
+      (!full_rows && (r_pad % 64 != 0 || r_pad < r))) {
+    set_error("apla_engine_create: invalid configuration (B=%d N=%d D=%d H=%d L=%d hidden=%d C=%d patch=%d img=%d kpad=%d "
+              "r=%d r_pad=%d full_rows=%d)", B, N, D, H, L, hidden, C, patch, img, kpad, r, r_pad, full_rows);
+    return nullptr;
+  }
+  Engine* e = new Engine();
+  e->B = B; e->N = N; e->D = D; e->H = H; e->L = L; e->hidden = hidden; e->C = C; e->P = N - 1; e->patch = patch;
+  e->img = img; e->kpad = kpad; e->r = r; e->r_pad = r_pad; e->full_rows = full_rows; e->eps = eps; e->scale = scale;
+  e->blk.resize(L);
+  return e;
+}
+
+void apla_engine_destroy(apla_engine_t h) { delete reinterpret_cast<Engine*>(h); }
+
+/* block < 0: global buffer `name`; otherwise per-block pointer `name` of block `block`. */
+int apla_engine_set_ptr(apla_engine_t h, const char* name, int block, void* p) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  APLA_CHECK(e != nullptr && name != nullptr, "apla_engine_set_ptr: null handle or name");
+  const std::string n(name);
+  if (block < 0) {
+    bool known = false;
+    for (const char* k : kGlobalNames) known |= (n == k);
+    APLA_CHECK(known, "apla_engine_set_ptr: unknown global buffer '%s'", name);
+    e->g[n] = p;
+    return 0;
+  }
+  APLA_CHECK(block < e->L, "apla_engine_set_ptr: block %d out of range", block);
+  BlockPtrs& b = e->blk[block];
+#define SETP(field)                                              \
+  if (n == #field) {                                             \
+    b.field = reinterpret_cast<decltype(b.field)>(p);            \
+    return 0;                                                    \
+  }
+  SETP(wqkv) SETP(wqkvT) SETP(wfc1) SETP(wfc1T) SETP(wfc2) SETP(wfc2T) SETP(wproj) SETP(wprojT) SETP(bqkv) SETP(bfc1)
+  SETP(bfc2) SETP(ln1w) SETP(ln1b) SETP(ln2w) SETP(ln2b) SETP(g1) SETP(g2) SETP(bproj) SETP(qkv) SETP(ao) SETP(hpre)
+  SETP(lse)
+#undef SETP
+  set_error("apla_engine_set_ptr: unknown block pointer '%s'", name);
+  return 1;
+}
+
+int64_t apla_engine_arena_size(apla_engine_t h) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  return e ? arena_of(e).n : -1;
+}
+int64_t apla_engine_arena_decay_size(apla_engine_t h) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  return e ? arena_of(e).n_decay : -1;
+}
+
+int apla_engine_forward(apla_engine_t h, const float* images, const int64_t* labels, float loss_scale, float grad_scale,
+                        apla_stream_t stream) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  APLA_CHECK(e != nullptr && images != nullptr, "apla_engine_forward: null handle or images");
+  return engine_forward(e, images, labels, loss_scale, grad_scale, reinterpret_cast<cudaStream_t>(stream));
+}
+int apla_engine_backward(apla_engine_t h, int block_from, int block_to, apla_stream_t stream) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  APLA_CHECK(e != nullptr, "apla_engine_backward: null handle");
+  return engine_backward(e, block_from, block_to, reinterpret_cast<cudaStream_t>(stream));
+}
+int apla_engine_optim(apla_engine_t h, float gscale, float max_norm, float lr, float wd, float beta1, float beta2,
+                      float eps, int step, apla_stream_t stream) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  APLA_CHECK(e != nullptr, "apla_engine_optim: null handle");
+  return engine_optim(e, gscale, max_norm, lr, wd, beta1, beta2, eps, step, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

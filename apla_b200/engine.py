@@ -1,0 +1,314 @@
+"""`FineTuneEngine`: host side of the native step engine (csrc/engine.cu).
+
+Takes a classifier built the reference way (`Classifier`: backbone ViT with APLA attention + `fc` head,
+src/defaults/models.py:24-92; here usually `hostvit.HostClassifier`), lays its tensors out for the B200 and runs
+`Trainer.global_step` (src/defaults/trainer.py:106-138) -- forward, CrossEntropy, backward restricted to the APLA
+rows and the head, data-parallel gradient mean, clip_grad_norm_(1.0), AdamW -- as native kernel launches.
+
+PyTorch's role here is plumbing only: device allocation (torch tensors own every buffer), the one-time conversion
+of frozen fp32 weights into bf16 [out,in] / [in,out] copies, stream handles and torch.distributed/NCCL for the
+gradient all-reduce.  All step arithmetic is in libapla_b200.so; nothing falls back to torch ops.
+
+Memory layout in HBM (T = B*N tokens, D embed, L blocks), sized for B=64 ViT-B/14 (~5 GB of 180 GB):
+  xs        fp32 [2L+1, T, D]   residual-stream checkpoints (block input / after attention / ... / final)
+  qkv[l]    bf16 [T, 3D]  ao[l] bf16 [T, D]  lse[l] fp32 [T, H]  hpre[l] bf16 [T, 4D]     saved for backward
+  ln_out, gelu_out, dx, dxb, dO, dqkv, dsub, delta                                         transients, reused
+  params / grads / exp_avg / exp_avg_sq   fp32 arenas [W1 x L | fc.weight | b1 x L | fc.bias]  (one all-reduce)
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from ._lib import LIB, ptr, require_device, stream
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _pad64(n: int) -> int:
+    return (n + 63) // 64 * 64
+
+
+def interpolate_pos_table(pos_embed: torch.Tensor, npatch: int) -> torch.Tensor:
+    """Bicubic resize of a [1, 1+n0, D] position table to an npatch grid (vit.py:421-437); done ONCE at engine
+    construction because pos_embed is frozen (the reference recomputes it every forward)."""
+    n0 = pos_embed.shape[1] - 1
+    if npatch == n0:
+        return pos_embed[0]
+    D = pos_embed.shape[-1]
+    s = int(math.sqrt(n0))
+    grid = pos_embed[:, 1:].reshape(1, s, s, D).permute(0, 3, 1, 2)
+    grid = nn.functional.interpolate(grid, scale_factor=math.sqrt(npatch / n0), mode="bicubic", align_corners=False,
+                                     recompute_scale_factor=False)
+    return torch.cat((pos_embed[:, :1], grid.permute(0, 2, 3, 1).reshape(1, -1, D)), dim=1)[0]
+
+
+class FineTuneEngine:
+    def __init__(self, model: nn.Module, batch_size: int, img_size: int, device="cuda", lr: float = 3e-5,
+                 weight_decay: float = 1e-5, clip: float = 1.0, betas=(0.9, 0.999), adam_eps: float = 1e-8,
+                 process_group=None):
+        require_device()
+        self.device = torch.device(device)
+        self.model = model
+        self.lr, self.wd, self.clip, self.betas, self.adam_eps = lr, weight_decay, clip, betas, adam_eps
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if self._dist_on() else 1
+        self.step_count = 0
+        self._keep: List[torch.Tensor] = []          # every device buffer the engine points at
+        self._handle = None
+        self._build(model, batch_size, img_size)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _dist_on(self) -> bool:
+        return torch.distributed.is_available() and torch.distributed.is_initialized()
+
+    def _dev(self, t: torch.Tensor, dtype) -> torch.Tensor:
+        out = t.detach().to(device=self.device, dtype=dtype).contiguous()
+        self._keep.append(out)
+        return out
+
+    def _new(self, *shape, dtype=BF16, zero=False) -> torch.Tensor:
+        t = (torch.zeros if zero else torch.empty)(*shape, dtype=dtype, device=self.device)
+        self._keep.append(t)
+        return t
+
+    def _set(self, name: str, t: Optional[torch.Tensor], block: int = -1):
+        LIB.call("apla_engine_set_ptr", self._handle, name.encode(), block, ptr(t))
+
+    def _build(self, model, B, img):
+        bb = model.backbone
+        conv = bb.patch_embed.proj
+        patch = conv.kernel_size[0]
+        D = bb.cls_token.shape[-1]
+        L = len(bb.blocks)
+        P = (img // patch) ** 2
+        N = P + 1
+        T = B * N
+        blk0 = bb.blocks[0]
+        H = blk0.attn.num_heads
+        hidden = blk0.mlp.fc1.out_features
+        C = model.fc.out_features
+        kpad = (3 * patch * patch + 63) // 64 * 64
+        self.stock_proj = hasattr(blk0.attn, "proj")            # multi-GPU 'full': stock attention, proj trainable
+        r = D if self.stock_proj else int(blk0.attn.partial_size)
+        full_rows = 1 if r > 128 else 0
+        r_pad = _pad64(r)
+        self.shape = dict(B=B, N=N, D=D, H=H, L=L, hidden=hidden, C=C, P=P, patch=patch, img=img, kpad=kpad, r=r,
+                          r_pad=r_pad, full_rows=full_rows, T=T)
+        eps = float(blk0.norm1.eps)
+        scale = float(blk0.attn.scale)
+        self._handle = LIB.load().apla_engine_create(B, N, D, H, L, hidden, C, patch, img, kpad, r, r_pad, full_rows,
+                                                     eps, scale)
+        if not self._handle:
+            raise RuntimeError("apla_engine_create failed: " + LIB.last_error())
+
+        # ---- embedding ----
+        wpe = torch.zeros(D, kpad, dtype=F32)
+        wpe[:, :3 * patch * patch] = conv.weight.detach().float().reshape(D, -1).cpu()
+        self._set("wpe", self._dev(wpe, BF16))
+        self._set("bpe", self._dev(conv.bias if conv.bias is not None else torch.zeros(D), F32))
+        self._set("cls", self._dev(bb.cls_token.reshape(D), F32))
+        self._set("pos", self._dev(interpolate_pos_table(bb.pos_embed.detach().float().cpu(), P), F32))
+        self._set("patches", self._new(B * P, kpad))
+        self._set("pe_out", self._new(B * P, D))
+
+        # ---- trainable arena ----
+        n = LIB.load().apla_engine_arena_size(self._handle)
+        self.n_arena = int(n)
+        self.params = self._new(n, dtype=F32, zero=True)
+        self.grads = self._new(n, dtype=F32, zero=True)
+        self.exp_avg = self._new(n, dtype=F32, zero=True)
+        self.exp_avg_sq = self._new(n, dtype=F32, zero=True)
+        self.sumsq = self._new(1, dtype=F32, zero=True)
+        o_w1, o_fcw = 0, L * r * D
+        o_b1 = o_fcw + C * D
+        o_fcb = o_b1 + L * r
+        self.offsets = dict(w1=o_w1, fcw=o_fcw, b1=o_b1, fcb=o_fcb, n=o_fcb + C)
+        assert self.offsets["n"] == n
+        self.slices: Dict[str, slice] = {}     # parameter name -> slice of the arena
+        self.shapes: Dict[str, tuple] = {}
+
+        idx_all = torch.zeros(L, r, dtype=torch.int32)
+        rowmap_all = torch.full((L, D), -1, dtype=torch.int32)
+        # ---- blocks ----
+        for l, blk in enumerate(bb.blocks):
+            at = blk.attn
+            pre = f"backbone.blocks.{l}."
+            if self.stock_proj:
+                inds = torch.arange(D)
+                w_full = at.proj.weight.detach().float().cpu()
+                b_full = at.proj.bias.detach().float().cpu()
+                w1, b1 = w_full, b_full
+                names = (pre + "attn.proj.weight", pre + "attn.proj.bias")
+            else:
+                inds = torch.as_tensor(at.indices).long().cpu()
+                w1 = at.proj_weight1.detach().float().cpu()
+                b1 = at.proj_bias1.detach().float().cpu()
+                w_full = torch.zeros(D, D)
+                b_full = torch.zeros(D)
+                w_full[inds[:r]] = w1
+                b_full[inds[:r]] = b1
+                if r < D:
+                    w_full[inds[r:]] = at.proj_weight2.detach().float().cpu()
+                    b_full[inds[r:]] = at.proj_bias2.detach().float().cpu()
+                names = (pre + "attn.proj_weight1", pre + "attn.proj_bias1")
+            idx_all[l] = inds[:r].to(torch.int32)
+            rowmap_all[l, inds[:r]] = torch.arange(r, dtype=torch.int32)
+            self.slices[names[0]] = slice(o_w1 + l * r * D, o_w1 + (l + 1) * r * D)
+            self.shapes[names[0]] = (r, D)
+            self.slices[names[1]] = slice(o_b1 + l * r, o_b1 + (l + 1) * r)
+            self.shapes[names[1]] = (r,)
+            self.params[self.slices[names[0]]] = w1.reshape(-1).to(self.device)
+            self.params[self.slices[names[1]]] = b1.to(self.device)
+
+            def lin(mod):
+                w = mod.weight.detach().float()
+                b = mod.bias.detach().float() if mod.bias is not None else torch.zeros(w.shape[0])
+                return self._dev(w, BF16), self._dev(w.t(), BF16), self._dev(b, F32)
+
+            wqkv, wqkvT, bqkv = lin(at.qkv)
+            wfc1, wfc1T, bfc1 = lin(blk.mlp.fc1)
+            wfc2, wfc2T, bfc2 = lin(blk.mlp.fc2)
+            for k, v in dict(wqkv=wqkv, wqkvT=wqkvT, bqkv=bqkv, wfc1=wfc1, wfc1T=wfc1T, bfc1=bfc1, wfc2=wfc2,
+                             wfc2T=wfc2T, bfc2=bfc2, wproj=self._dev(w_full, BF16), wprojT=self._dev(w_full.t(), BF16),
+                             bproj=self._dev(b_full, F32), ln1w=self._dev(blk.norm1.weight, F32),
+                             ln1b=self._dev(blk.norm1.bias, F32), ln2w=self._dev(blk.norm2.weight, F32),
+                             ln2b=self._dev(blk.norm2.bias, F32)).items():
+                self._set(k, v, l)
+            g1 = getattr(blk.ls1, "gamma", None)
+            g2 = getattr(blk.ls2, "gamma", None)
+            self._set("g1", self._dev(g1, F32) if g1 is not None else None, l)
+            self._set("g2", self._dev(g2, F32) if g2 is not None else None, l)
+            self._set("qkv", self._new(T, 3 * D), l)
+            self._set("ao", self._new(T, D), l)
+            self._set("hpre", self._new(T, hidden), l)
+            self._set("lse", self._new(T, H, dtype=F32), l)
+
+        # ---- head ----
+        self.slices["fc.weight"] = slice(o_fcw, o_fcw + C * D)
+        self.shapes["fc.weight"] = (C, D)
+        self.slices["fc.bias"] = slice(o_fcb, o_fcb + C)
+        self.shapes["fc.bias"] = (C,)
+        self.params[self.slices["fc.weight"]] = model.fc.weight.detach().float().reshape(-1).to(self.device)
+        self.params[self.slices["fc.bias"]] = model.fc.bias.detach().float().to(self.device)
+        self._set("lnfw", self._dev(bb.norm.weight, F32))
+        self._set("lnfb", self._dev(bb.norm.bias, F32))
+
+        # ---- globals ----
+        self.xs = self._new(2 * L + 1, T, D, dtype=F32)
+        self.logits = self._new(B, C, dtype=F32)
+        self.loss = self._new(1, dtype=F32, zero=True)
+        self.idx = self._dev(idx_all, torch.int32)
+        for name, t in dict(xs=self.xs, ln_out=self._new(T, D), gelu_out=self._new(T, hidden),
+                            dx=self._new(T, D, dtype=F32), dxb=self._new(T, D), dO=self._new(T, D),
+                            dqkv=self._new(T, 3 * D), delta=self._new(T, H, dtype=F32),
+                            cls_ln=self._new(B, D), logits=self.logits, dlogits=self._new(B, C, dtype=F32),
+                            loss=self.loss, dcls=self._new(B, D), params=self.params, grads=self.grads,
+                            exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq, idx=self.idx, sumsq=self.sumsq).items():
+            self._set(name, t)
+        if full_rows:
+            self._set("rowmap", self._dev(rowmap_all, torch.int32))
+        else:
+            self._set("dsub", self._new(T, r_pad))
+        self.images_dev = self._new(B, 3, img, img, dtype=F32)
+        self.labels_dev = self._new(B, dtype=torch.int64)
+        self._ar_stream = torch.cuda.Stream(device=self.device) if self.world > 1 else None
+        torch.cuda.synchronize(self.device)
+
+    def __del__(self):
+        try:
+            if self._handle:
+                LIB.load().apla_engine_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------------------------
+    def trainable_names(self) -> List[str]:
+        """Same order as the reference's named_parameters() filter (I5/I7 of SURVEY.md 4.2)."""
+        L = self.shape["L"]
+        w, b = ("attn.proj.weight", "attn.proj.bias") if self.stock_proj else ("attn.proj_weight1", "attn.proj_bias1")
+        out = []
+        for l in range(L):
+            out += [f"backbone.blocks.{l}.{w}", f"backbone.blocks.{l}.{b}"]
+        return out + ["fc.weight", "fc.bias"]
+
+    def named_grads(self) -> Dict[str, torch.Tensor]:
+        return {k: self.grads[self.slices[k]].view(self.shapes[k]) for k in self.trainable_names()}
+
+    def named_params(self) -> Dict[str, torch.Tensor]:
+        return {k: self.params[self.slices[k]].view(self.shapes[k]) for k in self.trainable_names()}
+
+    def sync_to_model(self):
+        """Write the arena's fp32 parameters back into the nn.Module (state_dict / checkpoint compatibility)."""
+        sd = dict(self.model.named_parameters())
+        with torch.no_grad():
+            for k, v in self.named_params().items():
+                sd[k].copy_(v.to(sd[k].device))
+
+    # ------------------------------------------------------------------------------------------------------------
+    def forward(self, images: torch.Tensor, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """images fp32 [B,3,S,S] on the engine's device -> logits fp32 [B,C] (and loss/dlogits when labels given)."""
+        B = self.shape["B"]
+        if images.shape != self.images_dev.shape or images.dtype != F32 or not images.is_cuda:
+            raise RuntimeError(f"images must be a CUDA fp32 tensor of shape {tuple(self.images_dev.shape)}")
+        if labels is not None and (labels.dtype != torch.int64 or labels.shape != (B,) or not labels.is_cuda):
+            raise RuntimeError("labels must be a CUDA int64 tensor of shape [B]")
+        images = images.contiguous()
+        # CrossEntropyLoss(mean) over the local batch (wrappers.py:314); DDP later averages gradients over ranks
+        LIB.call("apla_engine_forward", self._handle, ptr(images), ptr(labels), 1.0 / B, 1.0 / B, stream())
+        return self.logits
+
+    def backward(self):
+        L = self.shape["L"]
+        if self.world == 1:
+            LIB.call("apla_engine_backward", self._handle, L - 1, 0, stream())
+            return
+        # data parallel: reduce the upper blocks' gradients (plus fc.weight, contiguous with them in the arena)
+        # on a side stream while the lower blocks are still in backward
+        half = L // 2
+        o = self.offsets
+        r, D = self.shape["r"], self.shape["D"]
+        cur = torch.cuda.current_stream()
+        LIB.call("apla_engine_backward", self._handle, L - 1, half, stream())
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        with torch.cuda.stream(self._ar_stream):
+            self._ar_stream.wait_event(ev)
+            torch.distributed.all_reduce(self.grads[o["w1"] + half * r * D:o["b1"]], group=self.pg)
+        if half > 0:
+            LIB.call("apla_engine_backward", self._handle, half - 1, 0, stream())
+        ev2 = torch.cuda.Event()
+        ev2.record(cur)
+        with torch.cuda.stream(self._ar_stream):
+            self._ar_stream.wait_event(ev2)
+            if half > 0:
+                torch.distributed.all_reduce(self.grads[o["w1"]:o["w1"] + half * r * D], group=self.pg)
+            torch.distributed.all_reduce(self.grads[o["b1"]:o["n"]], group=self.pg)
+        cur.wait_stream(self._ar_stream)
+
+    def optim_step(self):
+        self.step_count += 1
+        LIB.call("apla_engine_optim", self._handle, 1.0 / self.world, float(self.clip or 0.0), self.lr, self.wd,
+                 self.betas[0], self.betas[1], self.adam_eps, self.step_count, stream())
+
+    def step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """One Trainer.global_step on device-resident inputs; returns the (device) loss scalar."""
+        self.forward(images, labels)
+        self.backward()
+        self.optim_step()
+        return self.loss
+
+    def step_from_host(self, images_pinned: torch.Tensor, labels_pinned: torch.Tensor) -> float:
+        """The end-to-end call: pinned host batch -> H2D -> step -> loss read back to the host."""
+        self.images_dev.copy_(images_pinned, non_blocking=True)
+        self.labels_dev.copy_(labels_pinned, non_blocking=True)
+        loss = self.step(self.images_dev, self.labels_dev)
+        return float(loss.item())
+
+    def grad_norm(self) -> torch.Tensor:
+        """sqrt of the sum of squares the last optim_step clipped with (after the 1/world scaling)."""
+        return self.sumsq.sqrt()

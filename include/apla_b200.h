@@ -115,6 +115,31 @@ int apla_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, int
 int apla_proj_refresh(const float* w1, const float* b1, const int32_t* idx, void* wfull, void* wfullT, float* bfull,
                       int L, int r, int D, int64_t w1_block_stride, int64_t b1_block_stride, apla_stream_t stream);
 
+/* --- step engine: the whole fine-tune step as one native call sequence ------------------------------------ */
+/* Replaces Trainer.global_step's device work (src/defaults/trainer.py:106-138): Classifier.forward
+ * (src/defaults/models.py:81-92), CrossEntropyLoss, loss.backward() restricted to the APLA rows + head,
+ * clip_grad_norm_ and AdamW.  The engine owns no memory; every buffer is a caller-allocated device pointer
+ * registered by name (global: block = -1; per block: block = 0..L-1).  See apla_b200/engine.py for the table. */
+typedef void* apla_engine_t;
+apla_engine_t apla_engine_create(int B, int N, int D, int H, int L, int hidden, int C, int patch, int img, int kpad,
+                                 int r, int r_pad, int full_rows, float eps, float scale);
+void apla_engine_destroy(apla_engine_t e);
+int apla_engine_set_ptr(apla_engine_t e, const char* name, int block, void* p);
+/* Trainable arena layout (fp32): [proj_weight1 x L | fc.weight | proj_bias1 x L | fc.bias]; the first
+ * apla_engine_arena_decay_size() elements are weight-decayed (src/defaults/wrappers.py:205-221). */
+int64_t apla_engine_arena_size(apla_engine_t e);
+int64_t apla_engine_arena_decay_size(apla_engine_t e);
+/* logits (+ loss and dlogits when labels != NULL): loss += loss_scale * sum CE, dlogits *= grad_scale. */
+int apla_engine_forward(apla_engine_t e, const float* images, const int64_t* labels, float loss_scale,
+                        float grad_scale, apla_stream_t stream);
+/* Backward through blocks block_from, block_from-1, ..., block_to (block_from == L-1 also zeroes the gradient arena
+ * and runs the head / final-norm backward first).  Splitting the range lets the host start the data-parallel
+ * all-reduce of the upper blocks' gradients while the lower blocks are still running. */
+int apla_engine_backward(apla_engine_t e, int block_from, int block_to, apla_stream_t stream);
+/* clip + AdamW over the arena, then refresh of the dense bf16 projection copies */
+int apla_engine_optim(apla_engine_t e, float gscale, float max_norm, float lr, float wd, float beta1, float beta2,
+                      float eps, int step, apla_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

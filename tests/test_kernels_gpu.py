@@ -225,3 +225,71 @@ def test_attention_varlen():
     ref.backward(dout.float())
     dqkv = ops.attn_bwd(qkv, out, dout, lse, H, scale, len(seqlens), max(seqlens), cu_seqlens=cu)
     assert rel(dqkv.float(), q32.grad) < 1e-2
+
+
+def test_clip_adamw_arena_matches_torch():
+    """grad_sumsq + adamw_step over an arena == clip_grad_norm_ + torch.optim.AdamW (two groups), fp32."""
+    _cuda()
+    from apla_b200._lib import LIB, ptr, stream
+    g = torch.Generator(device="cuda").manual_seed(8)
+    n, n_decay = 100_003, 90_000
+    p0 = torch.randn(n, device="cuda", generator=g) * 0.02
+    ours = p0.clone(); m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+    ss = torch.zeros(1, device="cuda")
+    pa = torch.nn.Parameter(p0[:n_decay].clone()); pb = torch.nn.Parameter(p0[n_decay:].clone())
+    opt = torch.optim.AdamW([{"params": [pa]}, {"params": [pb], "weight_decay": 0.0}], lr=3e-5, weight_decay=1e-5)
+    for step in range(1, 4):
+        grad = torch.randn(n, device="cuda", generator=g) * (3.0 if step == 1 else 1e-3)   # clipped / not clipped
+        world = 2.0
+        LIB.call("apla_grad_sumsq", ptr(grad), n, 1.0 / world, ptr(ss), stream())
+        LIB.call("apla_adamw_step", ptr(ours), ptr(grad), ptr(m), ptr(v), n, n_decay, ptr(ss), 1.0 / world, 1.0, 3e-5,
+                 1e-5, 0.9, 0.999, 1e-8, step, stream())
+        pa.grad = grad[:n_decay] / world; pb.grad = grad[n_decay:] / world
+        gn = torch.nn.utils.clip_grad_norm_([pa, pb], 1.0)
+        opt.step()
+        assert abs(float(ss.sqrt()) - float(gn)) <= 1e-5 * float(gn)
+        ref = torch.cat([pa.detach(), pb.detach()])
+        assert rel(ours - p0, ref - p0) < 1e-4
+        assert rel(ours, ref) < 1e-6
+
+
+def test_head_and_cross_entropy():
+    _cuda()
+    from apla_b200._lib import LIB, ptr, stream
+    g = torch.Generator(device="cuda").manual_seed(9)
+    B, D, C = 16, 384, 555
+    xn = bf(torch.randn(B, D, device="cuda", generator=g))
+    W = torch.randn(C, D, device="cuda", generator=g) * 0.05
+    bias = torch.randn(C, device="cuda", generator=g) * 0.1
+    labels = torch.randint(0, C, (B,), device="cuda", generator=g)
+    logits = torch.empty(B, C, device="cuda"); dlog = torch.empty(B, C, device="cuda"); loss = torch.zeros(1, device="cuda")
+    LIB.call("apla_head_fwd", ptr(xn), ptr(W), ptr(bias), ptr(logits), B, D, C, stream())
+    LIB.call("apla_cross_entropy", ptr(logits), ptr(labels), ptr(dlog), ptr(loss), B, C, 1.0 / B, 1.0 / B, stream())
+    x32 = xn.float().requires_grad_(True); W32 = W.clone().requires_grad_(True); b32 = bias.clone().requires_grad_(True)
+    ref_logits = x32 @ W32.t() + b32
+    ref_loss = torch.nn.functional.cross_entropy(ref_logits, labels)
+    ref_loss.backward()
+    assert rel(logits, ref_logits) < 1e-5 and abs(float(loss) - float(ref_loss)) < 1e-5 * float(ref_loss)
+    dW = torch.empty(C, D, device="cuda"); db = torch.empty(C, device="cuda")
+    dxn = torch.empty(B, D, device="cuda", dtype=torch.bfloat16)
+    LIB.call("apla_head_bwd", ptr(dlog), ptr(xn), ptr(W), ptr(dW), ptr(db), ptr(dxn), B, D, C, stream())
+    assert rel(dW, W32.grad) < 1e-5 and rel(db, b32.grad) < 1e-5 and rel(dxn.float(), x32.grad) < 4e-3
+
+
+def test_patchify_assemble_match_conv():
+    _cuda()
+    from apla_b200._lib import LIB, ptr, stream
+    g = torch.Generator(device="cuda").manual_seed(10)
+    B, S, p, D = 3, 56, 14, 128
+    P, kk, kpad = (S // p) ** 2, 3 * p * p, 640
+    img = torch.randn(B, 3, S, S, device="cuda", generator=g)
+    patches = torch.empty(B * P, kpad, device="cuda", dtype=torch.bfloat16)
+    LIB.call("apla_patchify", ptr(img), ptr(patches), B, S, p, kpad, stream())
+    ref = torch.nn.functional.unfold(img, kernel_size=p, stride=p).transpose(1, 2).reshape(B * P, kk)
+    assert torch.equal(patches[:, :kk], ref.to(torch.bfloat16)) and float(patches[:, kk:].abs().sum()) == 0.0
+    pe = bf(torch.randn(B * P, D, device="cuda", generator=g))
+    cls = torch.randn(D, device="cuda", generator=g); pos = torch.randn(P + 1, D, device="cuda", generator=g)
+    x = torch.empty(B, P + 1, D, device="cuda")
+    LIB.call("apla_assemble_tokens", ptr(pe), ptr(cls), ptr(pos), ptr(x), B, P, D, stream())
+    want = torch.cat((cls.expand(B, 1, D), pe.float().view(B, P, D)), 1) + pos
+    assert torch.equal(x, want)
