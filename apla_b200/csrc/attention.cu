@@ -460,6 +460,7 @@ int attn_fwd(const void* qkv, void* out, float* lse, const int* cu_seqlens, int 
   attn_fwd_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
                                             reinterpret_cast<__nv_bfloat16*>(out), lse, cu_seqlens, max_seqlen, H, scale);
   APLA_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -471,16 +472,19 @@ int attn_bwd(const void* qkv, const void* out, const void* dout, const float* ls
   attn_delta_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(out), delta, n_chunks);
   APLA_CUDA(cudaGetLastError());
+  count_launch();
   dim3 grid(cdiv(max_seqlen, TS), num_seqs * H);
   attn_bwd_dkdv_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                  reinterpret_cast<const __nv_bfloat16*>(dout), lse, delta,
                                                  reinterpret_cast<__nv_bfloat16*>(dqkv), cu_seqlens, max_seqlen, H,
                                                  scale);
   APLA_CUDA(cudaGetLastError());
+  count_launch();
   attn_bwd_dq_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                reinterpret_cast<const __nv_bfloat16*>(dout), lse, delta,
                                                reinterpret_cast<__nv_bfloat16*>(dqkv), cu_seqlens, max_seqlen, H, scale);
   APLA_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

@@ -12,6 +12,7 @@ extern "C" {
 
 const char* apla_last_error(void) { return get_error(); }
 int apla_version(void) { return 100; }
+int64_t apla_launch_count(void) { return launch_count(); }
 
 int apla_device_check(void) {
   int dev = 0, major = 0, minor = 0;

@@ -54,6 +54,10 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t row
   return 0;
 }
 
+static long long g_launches = 0;
+void count_launch(int n) { g_launches += n; }
+long long launch_count() { return g_launches; }
+
 int sm_count() {
   static int n = 0;
   if (!n) {

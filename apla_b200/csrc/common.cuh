@@ -36,6 +36,10 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t row
 
 int sm_count();
 
+// number of kernels launched by this library since load (bench.py reports the per-step delta as gpu_launches)
+void count_launch(int n = 1);
+long long launch_count();
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace apla

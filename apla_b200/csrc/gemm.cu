@@ -308,6 +308,7 @@ static int launch(const void* A, const void* B, int M, int N, int K, int lda, in
   const int grid = tiles < sm_count() ? tiles : sm_count();
   kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, M, N, K, k_splits, ep);
   APLA_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

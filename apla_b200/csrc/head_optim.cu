@@ -163,6 +163,7 @@ int head_fwd(const void* xn, const float* W, const float* bias, float* logits, i
   head_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(xn), W, bias,
                                                                     logits, B, D, C);
   APLA_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -171,6 +172,7 @@ int cross_entropy(const float* logits, const int64_t* labels, float* dlogits, fl
   APLA_CHECK(B > 0 && C > 0, "cross_entropy: empty");
   ce_kernel<<<B, 256, 0, s>>>(logits, labels, dlogits, loss, C, grad_scale, loss_scale);
   APLA_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -179,8 +181,10 @@ int head_bwd(const float* dlogits, const void* xn, const float* W, float* dW, fl
   APLA_CHECK(B > 0 && D > 0 && C > 0, "head_bwd: empty");
   head_wgrad_kernel<<<cdiv(C * D, 256), 256, 0, s>>>(dlogits, reinterpret_cast<const __nv_bfloat16*>(xn), dW, db, B, D, C);
   APLA_CUDA(cudaGetLastError());
+  count_launch();
   head_dgrad_kernel<<<cdiv(B * D, 256), 256, 0, s>>>(dlogits, W, reinterpret_cast<__nv_bfloat16*>(dxn), B, D, C);
   APLA_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -190,6 +194,7 @@ int grad_sumsq(const float* g, int64_t n, float scale, float* out, cudaStream_t 
   const int grid = (int)((n + 1023) / 1024 < 592 ? (n + 1023) / 1024 : 592);
   sumsq_kernel<<<grid, 256, 0, s>>>(g, n, scale, out);
   APLA_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -203,6 +208,7 @@ int adamw_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t 
   adamw_kernel<<<grid, 256, 0, s>>>(p, g, m, v, n, n_decay, sumsq, gscale, max_norm, lr, wd, b1, b2, eps, (float)bc1,
                                     (float)sqrt(bc2));
   APLA_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -213,6 +219,7 @@ int proj_refresh(const float* w1, const float* b1, const int* idx, void* wfull, 
                                                  reinterpret_cast<__nv_bfloat16*>(wfullT), bfull, L, r, D,
                                                  w1_block_stride, b1_block_stride);
   APLA_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

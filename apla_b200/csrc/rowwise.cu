@@ -233,6 +233,7 @@ int layernorm_fwd(const float* x, int64_t ldx, const float* w, const float* b, v
   LN_DISPATCH(D / 128, (ln_fwd_kernel<NV><<<grid, 256, 0, stream>>>(x, ldx, w, b, reinterpret_cast<__nv_bfloat16*>(y),
                                                                     ldy, rows, eps)));
   APLA_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -251,6 +252,7 @@ int layernorm_bwd(const void* dy, int64_t ld_dy, const float* x, int64_t ldx, co
                            reinterpret_cast<__nv_bfloat16*>(dxb), ld_dxb, gamma, reinterpret_cast<__nv_bfloat16*>(sub),
                            ld_sub, idx, r, r_pad, rows, eps)));
   APLA_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -261,6 +263,7 @@ int gather_cols(const void* dy, int64_t ld, void* sub, int64_t ld_sub, const int
   gather_cols_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), ld, reinterpret_cast<__nv_bfloat16*>(sub), ld_sub, idx, r, r_pad, rows);
   APLA_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -271,6 +274,7 @@ int colsum(const void* a, int64_t ld, int rows, int n, float* out, const int* ro
   colsum_kernel<<<grid, dim3(32, 8), 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a), ld, rows, n, out, rowmap,
                                                   rows_per_block);
   APLA_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -280,6 +284,7 @@ int patchify(const float* img, void* out, int B, int S, int p, int kpad, cudaStr
   const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   patchify_kernel<<<grid, 256, 0, stream>>>(img, reinterpret_cast<__nv_bfloat16*>(out), B, S, p, kpad);
   APLA_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -290,6 +295,7 @@ int assemble_tokens(const void* patch, const float* cls, const float* pos, float
   const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   assemble_tokens_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(patch), cls, pos, x, B, P, D);
   APLA_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py -- the APLA fine-tune step on B200 (BASELINE.json configs[1]: ViT-B/14, partial_size=8, 224 px,
+555 classes, batch 64 per GPU, bf16 compute, synthetic data, seeded random-init weights of that architecture).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] ...                # the reference algorithm on the host CPU cores
+
+One step = Trainer.global_step (src/defaults/trainer.py:106-138): forward, CrossEntropy, backward (weight
+gradients only for the APLA projection rows + head), data-parallel gradient mean, clip_grad_norm_(1.0), AdamW.
+Prints ONE JSON line (rank 0).  `value` = whole-job images/s with the batch resident in HBM; `e2e` = the same
+through the public API from pinned host buffers (H2D of the batch and D2H of the loss inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ViT-B/14 APLA fine-tune images/sec/GPU at 1/2/4/8 B200; % bf16 tensor roofline"
+WORKLOAD = dict(arch="vit_base", img=224, table_img=518, patch=14, n_classes=555, partial_size=8, batch_per_gpu=64)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(tflops_burst=d["bf16_tflops"], tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    hbm_gbs=d["hbm_gbs"], source="measured")
+    return dict(tflops_burst=1590.0, tflops_sustained=1400.0, hbm_gbs=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU during the timed region (NVML, else nvidia-smi)."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
+
+    def _loop(self):
+        nv = self._nvml
+        names = {}
+        if nv is not None:
+            for k in dir(nv):
+                if k.startswith("nvmlClocksEventReason") or k.startswith("nvmlClocksThrottleReason"):
+                    v = getattr(nv, k)
+                    if isinstance(v, int) and v not in (0,):
+                        names.setdefault(v, k.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", ""))
+        while not self._stop.is_set():
+            try:
+                if nv is not None:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                    try:
+                        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                    except Exception:
+                        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                    for bit, nm in names.items():
+                        if mask & bit and bit & (bit - 1) == 0:
+                            self.reasons.add(nm)
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}",
+                                          "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.active",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                    f = [x.strip() for x in out.stdout.strip().split(",")]
+                    self.samples.append(int(f[0]))
+                    self.max_mhz = int(f[1])
+                    self.reasons.add(f[2])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=2)
+        s = sorted(self.samples)
+        rs = sorted(r for r in self.reasons if r and r.lower() not in ("none", "gpuidle", "applicationsclockssetting"))
+        return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz, reasons=rs, samples=len(s))
+
+
+def synthetic_batch(batch, img, n_classes, seed=1234, rank=0):
+    import torch
+    g = torch.Generator().manual_seed(seed + rank)
+    return torch.randn(batch, 3, img, img, generator=g), torch.randint(0, n_classes, (batch,), generator=g)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port) on the host cores
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_steps(steps, warmup, batch):
+    """Times oracle.fine_tune_step (fp32 restatement of the reference step) on `batch` images of the workload."""
+    import torch
+    from oracle import apla_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    w = WORKLOAD
+    cfg = O.VitCfg(**O.VIT_B14, n_classes=w["n_classes"], partial_size=w["partial_size"])
+    sd = O.build_state(cfg, seed=0)
+    images, labels = O.synthetic_batch(batch, w["img"], w["n_classes"])
+    st = O.AdamWState()
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.fine_tune_step(sd, cfg, images, labels, st)
+        ts.append(time.perf_counter() - t0)
+    ts = ts[warmup:]
+    sec = sum(ts) / len(ts)
+    return dict(value=batch / sec, unit="images/s", cores=threads, kind="port",
+                sample=f"oracle/apla_oracle.py fine_tune_step, ViT-B/14 r=8 224px fp32, batch {batch}, "
+                       f"{len(ts)} steps after {warmup} warm-up, {sec * 1e3:.0f} ms/step"), sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 2))
+    cb, sec = cpu_reference_steps(steps, warmup, batch=8)
+    line = dict(metric=METRIC, value=cb["value"], unit="images/s", n_gpus=args.gpus, steps=steps, warmup=warmup,
+                ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=dict(workload="ViT-B/14 dinov2-arch APLA partial_size=8 fine-tune step, 224px, 555 classes; CPU "
+                                     "sample: batch 8 per step", **WORKLOAD),
+                cpu_baseline=cb,
+                e2e=dict(value=cb["value"], unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------
+def time_dominant_kernel(eng, torch, iters=24):
+    """CUDA-event timing of the dominant kernel as the step launches it: the Mlp.fc1 GEMM (+bias+GELU epilogue,
+    [T,768]x[768,3072]) -- rotating over the 12 blocks' weights/outputs so operands come from HBM, not L2."""
+    from apla_b200 import ops
+    sh = eng.shape
+    T, D, Hd, L = sh["T"], sh["D"], sh["hidden"], sh["L"]
+    x = torch.randn(T, D, device="cuda").to(torch.bfloat16)
+    ws = [(torch.randn(Hd, D, device="cuda") * 0.02).to(torch.bfloat16) for _ in range(4)]
+    hs = [torch.empty(T, Hd, device="cuda", dtype=torch.bfloat16) for _ in range(4)]
+    gs = [torch.empty(T, Hd, device="cuda", dtype=torch.bfloat16) for _ in range(4)]
+    bias = torch.zeros(Hd, device="cuda")
+    for i in range(4):
+        ops.gemm_bias_gelu(x, ws[i], bias, h=hs[i], g=gs[i])
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(iters):
+        ops.gemm_bias_gelu(x, ws[i % 4], bias, h=hs[i % 4], g=gs[i % 4])
+    b.record()
+    torch.cuda.synchronize()
+    sec = a.elapsed_time(b) * 1e-3 / iters
+    return dict(kernel="gemm_kernel<256,EPI_BIAS_GELU> (Mlp.fc1+GELU, 16448x3072x768)", us=sec * 1e6,
+                tflops=2.0 * T * D * Hd / sec / 1e12)
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from apla_b200._lib import LIB
+    from apla_b200.config import AplaConfig
+    from apla_b200.engine import FineTuneEngine
+    from apla_b200.flops import flops_per_image
+    from apla_b200.hostvit import ARCHS, build_classifier
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.gpus != world:
+        raise RuntimeError(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 through torch.distributed.run")
+    w = WORKLOAD
+    B = args.batch or w["batch_per_gpu"]
+
+    # identical weights and APLA indices on every rank: same seed, same constructor order
+    model = build_classifier(w["arch"], img_size=w["table_img"], patch_size=w["patch"], n_classes=w["n_classes"],
+                             apla_config=AplaConfig(w["partial_size"]), seed=0)
+    eng = FineTuneEngine(model, batch_size=B, img_size=w["img"], device=f"cuda:{local}")
+    images, labels = synthetic_batch(B, w["img"], w["n_classes"], rank=rank)
+    images_pin, labels_pin = images.pin_memory(), labels.pin_memory()
+    images_dev, labels_dev = images.cuda(), labels.cuda()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0 = LIB.load().apla_launch_count()
+    eng.step(images_dev, labels_dev)
+    launches_per_step = int(LIB.load().apla_launch_count() - n0)
+    if sampler:
+        sampler.start()
+    ms_step = timed(lambda: eng.step(images_dev, labels_dev), args.steps, max(0, args.warmup - 1))
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = timed(lambda: eng.step_from_host(images_pin, labels_pin), args.steps, max(1, args.warmup // 2))
+    loss = float(eng.loss.item())
+
+    if rank == 0:
+        peaks = load_peaks()
+        a = ARCHS[w["arch"]]
+        f_fwd, f_bwd = flops_per_image(a.embed_dim, a.depth, w["patch"], w["img"], w["partial_size"], w["n_classes"])
+        flops_step = (f_fwd + f_bwd) * B
+        achieved = flops_step / (ms_step * 1e-3) / 1e12
+        dom = time_dominant_kernel(eng, torch)
+        line = dict(
+            metric=METRIC, value=B * world / (ms_step * 1e-3), unit="images/s", n_gpus=world, steps=args.steps,
+            warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype="bf16", data="synthetic", per_gpu=B / (ms_step * 1e-3), loss=loss,
+            config=dict(workload="ViT-B/14 dinov2-arch (518-px pos table, LayerScale, qkv bias) APLA partial_size=8 "
+                                 "supervised fine-tune step, 224px, 555 classes, AdamW lr 3e-5 wd 1e-5 clip 1.0",
+                        global_batch=B * world, batch_per_gpu=B, tokens_per_image=257, parallelism=f"dp{world}",
+                        l2="per-step working set ~5 GB >> 126 MB L2 (activations of 12 blocks), no flush needed",
+                        **{k: v for k, v in w.items() if k != "batch_per_gpu"}),
+            roofline=dict(bound="tensor", scope="whole step (all kernels), algorithmic FLOPs of SURVEY.md App. B",
+                          achieved=achieved, peak=peaks["tflops_sustained"], unit="TFLOP/s",
+                          frac=achieved / peaks["tflops_sustained"], frac_of_burst=achieved / peaks["tflops_burst"],
+                          peak_source=f"{peaks['source']} (sustained cuBLAS bf16; burst {peaks['tflops_burst']})",
+                          flops_per_step=flops_step, traffic=None,
+                          dominant_kernel=dict(**dom, frac_of_burst=dom["tflops"] / peaks["tflops_burst"])),
+            e2e=dict(value=B * world / (ms_e2e * 1e-3), unit="images/s", ms_per_step=ms_e2e,
+                     h2d_bytes_per_step=images_pin.numel() * 4 + labels_pin.numel() * 8, d2h_bytes_per_step=4),
+            gpu_launches=launches_per_step * args.steps, gpu_launches_per_step=launches_per_step, clocks=clocks)
+        if world == 1 and not args.no_cpu:
+            cb, _ = cpu_reference_steps(steps=3, warmup=1, batch=8)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (default: the workload's 64)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

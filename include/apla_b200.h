@@ -24,6 +24,8 @@ typedef void* apla_stream_t; /* cudaStream_t */
 /* --- library ------------------------------------------------------------------------------------------- */
 const char* apla_last_error(void);
 int apla_version(void);
+/* kernels launched by this library since it was loaded (every launcher counts its own launches) */
+int64_t apla_launch_count(void);
 /* 0 iff the current device is compute capability 10.x (B200); the product path has no other backend. */
 int apla_device_check(void);
 
