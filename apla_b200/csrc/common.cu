@@ -34,20 +34,26 @@ static EncodeTiledFn encode_fn() {
 
 int make_tmap_2d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows, uint32_t box_cols, bool swizzle128) {
+  return make_tmap_2d_sw(out, base, elt_bytes, rows, cols, ld, box_rows, box_cols, swizzle128 ? 128 : 0);
+}
+
+int make_tmap_2d_sw(CUtensorMap* out, const void* base, int elt_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
+                    uint32_t box_rows, uint32_t box_cols, int swizzle_bytes) {
   EncodeTiledFn fn = encode_fn();
   APLA_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
   APLA_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor-map base %p is not 16-byte aligned", base);
   APLA_CHECK((ld * elt_bytes) % 16 == 0, "tensor-map row pitch %llu B is not a multiple of 16",
              (unsigned long long)(ld * elt_bytes));
   APLA_CHECK(box_rows <= 256 && box_cols <= 256, "tensor-map box %ux%u exceeds 256", box_rows, box_cols);
-  if (swizzle128) APLA_CHECK(box_cols * elt_bytes == 128, "128B swizzle needs a 128-byte inner box");
+  if (swizzle_bytes) APLA_CHECK(int(box_cols * elt_bytes) == swizzle_bytes, "swizzle span must equal the inner box bytes");
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * (uint64_t)elt_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMapDataType dt = elt_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUresult r = fn(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                       : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   APLA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box=%ux%u)",
              (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);

@@ -33,6 +33,9 @@ const char* get_error();
 // box = box_rows x box_cols, 128-byte swizzle (box_cols * elt == 128 bytes) or none.
 int make_tmap_2d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows, uint32_t box_cols, bool swizzle128);
+// same with an explicit swizzle span in bytes (0, 64 or 128 = inner box bytes)
+int make_tmap_2d_sw(CUtensorMap* out, const void* base, int elt_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
+                    uint32_t box_rows, uint32_t box_cols, int swizzle_bytes);
 
 int sm_count();
 
