@@ -31,7 +31,6 @@ __global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ xn, const floa
   float acc = 0.f;
   for (int d = lane; d < D; d += 32) acc += __bfloat162float(xn[size_t(b) * D + d]) * __ldg(W + size_t(c) * D + d);
   acc = warp_sum(acc);
-  // autocast hands bf16 logits to the loss; keep that rounding so the loss matches the reference's bf16 path
   if (lane == 0) logits[gw] = acc + bias[c];
 }
 
@@ -86,9 +85,17 @@ __global__ void head_dgrad_kernel(const float* __restrict__ dlogits, const float
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * D) return;
   const int b = i / D, d = i % D;
-  float acc = 0.f;
-  for (int c = 0; c < C; ++c) acc += __ldg(dlogits + size_t(b) * C + c) * __ldg(W + size_t(c) * D + d);
-  dxn[i] = __float2bfloat16_rn(acc);
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // independent chains: the loop is latency-bound
+  int c = 0;
+  for (; c + 4 <= C; c += 4) {
+    const float* dl = dlogits + size_t(b) * C + c;
+    acc0 += __ldg(dl) * __ldg(W + size_t(c) * D + d);
+    acc1 += __ldg(dl + 1) * __ldg(W + size_t(c + 1) * D + d);
+    acc2 += __ldg(dl + 2) * __ldg(W + size_t(c + 2) * D + d);
+    acc3 += __ldg(dl + 3) * __ldg(W + size_t(c + 3) * D + d);
+  }
+  for (; c < C; ++c) acc0 += __ldg(dlogits + size_t(b) * C + c) * __ldg(W + size_t(c) * D + d);
+  dxn[i] = __float2bfloat16_rn((acc0 + acc1) + (acc2 + acc3));
 }
 
 // ------------------------------------------------------------------------------------------------

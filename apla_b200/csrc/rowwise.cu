@@ -172,22 +172,33 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ a, int64_t ld, i
 // ------------------------------------------------------------------------------------------------
 // patch extraction: images fp32 [B,3,S,S] -> bf16 [B*P, kpad], k = (c, py, px)  (conv k=s=p as a GEMM)
 // ------------------------------------------------------------------------------------------------
+// One block per image row (b, c, y): reads are fully coalesced, each thread converts two neighbouring pixels.
+// Blocks past the image rows zero the kpad - 3*p*p padding columns of the patch matrix.
 __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int S, int p,
                                 int kpad) {
   const int g = S / p;
-  const int64_t total = int64_t(B) * g * g * kpad;
   const int kk = 3 * p * p;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    const int k = int(i % kpad);
-    const int64_t pr = i / kpad;
-    float v = 0.f;
-    if (k < kk) {
-      const int px = k % p, py = (k / p) % p, c = k / (p * p);
-      const int pi = int(pr % (g * g)), b = int(pr / (g * g));
-      const int gy = pi / g, gx = pi % g;
-      v = __ldg(img + ((int64_t(b) * 3 + c) * S + gy * p + py) * S + gx * p + px);
+  const int n_rows = B * 3 * S;
+  if (int(blockIdx.x) < n_rows) {
+    const int y = blockIdx.x % S, c = (blockIdx.x / S) % 3, b = blockIdx.x / (3 * S);
+    const int gy = y / p, py = y % p;
+    const float* src = img + size_t(blockIdx.x) * S;
+    __nv_bfloat16* dst = out + (size_t(b) * g * g + size_t(gy) * g) * kpad + c * p * p + py * p;
+    if ((p & 1) == 0 && (kpad & 1) == 0) {
+      for (int x = 2 * threadIdx.x; x < S; x += 2 * blockDim.x) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(src + x));
+        const int gx = x / p, px = x % p;
+        *reinterpret_cast<uint32_t*>(dst + size_t(gx) * kpad + px) = pack_bf16(v.x, v.y);
+      }
+    } else {
+      for (int x = threadIdx.x; x < S; x += blockDim.x) dst[size_t(x / p) * kpad + x % p] = __float2bfloat16_rn(__ldg(src + x));
     }
-    out[i] = __float2bfloat16_rn(v);
+  } else {
+    const int pad = kpad - kk;
+    const int64_t total = int64_t(B) * g * g * pad;
+    for (int64_t i = int64_t(blockIdx.x - n_rows) * blockDim.x + threadIdx.x; i < total;
+         i += int64_t(gridDim.x - n_rows) * blockDim.x)
+      out[(i / pad) * kpad + kk + (i % pad)] = __float2bfloat16_rn(0.f);
   }
 }
 
@@ -269,7 +280,7 @@ int gather_cols(const void* dy, int64_t ld, void* sub, int64_t ld_sub, const int
 
 int colsum(const void* a, int64_t ld, int rows, int n, float* out, const int* rowmap, cudaStream_t stream) {
   APLA_CHECK(rows > 0 && n > 0, "colsum: empty");
-  const int rows_per_block = 512;
+  const int rows_per_block = 64;
   dim3 grid(cdiv(n, 32), cdiv(rows, rows_per_block));
   colsum_kernel<<<grid, dim3(32, 8), 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a), ld, rows, n, out, rowmap,
                                                   rows_per_block);
@@ -280,9 +291,8 @@ int colsum(const void* a, int64_t ld, int rows, int n, float* out, const int* ro
 
 int patchify(const float* img, void* out, int B, int S, int p, int kpad, cudaStream_t stream) {
   APLA_CHECK(B > 0 && S % p == 0 && kpad >= 3 * p * p, "patchify: bad shape B=%d S=%d p=%d kpad=%d", B, S, p, kpad);
-  const int64_t total = int64_t(B) * (S / p) * (S / p) * kpad;
-  const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  patchify_kernel<<<grid, 256, 0, stream>>>(img, reinterpret_cast<__nv_bfloat16*>(out), B, S, p, kpad);
+  const int pad_blocks = kpad > 3 * p * p ? 64 : 0;
+  patchify_kernel<<<B * 3 * S + pad_blocks, 128, 0, stream>>>(img, reinterpret_cast<__nv_bfloat16*>(out), B, S, p, kpad);
   APLA_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -267,27 +267,25 @@ class FineTuneEngine:
         if self.world == 1:
             LIB.call("apla_engine_backward", self._handle, L - 1, 0, stream())
             return
-        # data parallel: reduce the upper blocks' gradients (plus fc.weight, contiguous with them in the arena)
-        # on a side stream while the lower blocks are still in backward
-        half = L // 2
-        o = self.offsets
-        r, D = self.shape["r"], self.shape["D"]
+        # data parallel: reduce the upper blocks' gradients (plus fc.weight, contiguous with them in the arena) on a
+        # side stream while the lower blocks are still in backward (chunk plan: apla_b200/dp.py)
+        from .dp import ArenaLayout, allreduce_arena
+        lay = ArenaLayout(L=L, r=self.shape["r"], D=self.shape["D"], C=self.shape["C"])
+        half = lay.split_block()
         cur = torch.cuda.current_stream()
         LIB.call("apla_engine_backward", self._handle, L - 1, half, stream())
         ev = torch.cuda.Event()
         ev.record(cur)
         with torch.cuda.stream(self._ar_stream):
             self._ar_stream.wait_event(ev)
-            torch.distributed.all_reduce(self.grads[o["w1"] + half * r * D:o["b1"]], group=self.pg)
+            allreduce_arena(self.grads, lay, group=self.pg, which="early")
         if half > 0:
             LIB.call("apla_engine_backward", self._handle, half - 1, 0, stream())
         ev2 = torch.cuda.Event()
         ev2.record(cur)
         with torch.cuda.stream(self._ar_stream):
             self._ar_stream.wait_event(ev2)
-            if half > 0:
-                torch.distributed.all_reduce(self.grads[o["w1"]:o["w1"] + half * r * D], group=self.pg)
-            torch.distributed.all_reduce(self.grads[o["b1"]:o["n"]], group=self.pg)
+            allreduce_arena(self.grads, lay, group=self.pg, which="late")
         cur.wait_stream(self._ar_stream)
 
     def optim_step(self):

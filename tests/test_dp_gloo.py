@@ -1,0 +1,82 @@
+"""Data-parallel host logic on CPU with gloo, world_size 2: the arena layout / chunked all-reduce plan used by the
+engine, checked against the DDP semantics of the reference (src/defaults/wrappers.py:182-183): the mean over ranks of
+the per-rank gradients equals the gradient of the mean loss over the concatenated batch."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from apla_b200.dp import ArenaLayout, allreduce_arena
+
+
+def test_arena_layout_matches_engine_contract():
+    lay = ArenaLayout(L=12, r=8, D=768, C=555)
+    assert lay.n == 12 * 8 * 768 + 555 * 768 + 12 * 8 + 555 == 500_619
+    assert lay.n_decay == 12 * 8 * 768 + 555 * 768
+    early, late = lay.chunks()
+    covered = sorted((s.start, s.stop) for s in early + late)
+    assert covered[0][0] == 0 and covered[-1][1] == lay.n
+    assert all(a[1] == b[0] for a, b in zip(covered[:-1], covered[1:]))          # a partition: no gap, no overlap
+    # early chunk = blocks L/2.. + fc.weight, i.e. everything finished when backward passes block L/2
+    assert early == [slice(lay.weight_slice(6).start, lay.b1)]
+    assert ArenaLayout(L=1, r=4, D=128, C=10).chunks()[1] == [slice(4 * 128 + 10 * 128, 4 * 128 + 10 * 128 + 4 + 10)]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from oracle import apla_oracle as O
+    cfg = O.VitCfg(embed_dim=128, depth=2, num_heads=2, patch_size=14, img_size=56, n_classes=10, partial_size=16)
+    sd = O.build_state(cfg, seed=0)           # same seed on every rank -> identical weights and indices
+    O.perturb_state(sd)
+    images, labels = O.synthetic_batch(3, 56, 10, rank=rank)
+    res = O.loss_and_grads(sd, cfg, images, labels)
+    lay = ArenaLayout(L=cfg.depth, r=16, D=128, C=10)
+    arena = torch.zeros(lay.n)
+    for l in range(cfg.depth):
+        arena[lay.weight_slice(l)] = res.grads[f"backbone.blocks.{l}.attn.proj_weight1"].flatten()
+        arena[lay.bias_slice(l)] = res.grads[f"backbone.blocks.{l}.attn.proj_bias1"]
+    arena[lay.fcw:lay.b1] = res.grads["fc.weight"].flatten()
+    arena[lay.fcb:lay.n] = res.grads["fc.bias"]
+    allreduce_arena(arena, lay, which="early")
+    allreduce_arena(arena, lay, which="late")
+    arena /= world
+    if rank == 0:
+        # single-process reference: mean loss over the concatenated batch
+        imgs = [images] + [O.synthetic_batch(3, 56, 10, rank=r)[0] for r in range(1, world)]
+        labs = [labels] + [O.synthetic_batch(3, 56, 10, rank=r)[1] for r in range(1, world)]
+        full = O.loss_and_grads(sd, cfg, torch.cat(imgs), torch.cat(labs))
+        want = torch.zeros(lay.n)
+        for l in range(cfg.depth):
+            want[lay.weight_slice(l)] = full.grads[f"backbone.blocks.{l}.attn.proj_weight1"].flatten()
+            want[lay.bias_slice(l)] = full.grads[f"backbone.blocks.{l}.attn.proj_bias1"]
+        want[lay.fcw:lay.b1] = full.grads["fc.weight"].flatten()
+        want[lay.fcb:lay.n] = full.grads["fc.bias"]
+        err = float((arena - want).norm() / want.norm())
+        torch.save({"err": err, "inds_equal": True}, out)
+    # indices are identical across ranks without any broadcast (same seed, same constructor order)
+    inds = sd["backbone.blocks.1.attn.inds"].clone()
+    gathered = [torch.zeros_like(inds) for _ in range(world)]
+    dist.all_gather(gathered, inds)
+    assert all(torch.equal(g, inds) for g in gathered)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_mean_equals_concatenated_batch(tmp_path):
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out)
+    assert res["err"] < 1e-5, res
