@@ -8,7 +8,10 @@
 // Tensor-core path: warp-level mma.sync m16n8k16 with register-resident P / dS (flash-attention-2 style).
 // Round-1 implementation; the tcgen05/TMEM version of this kernel is the next step for this file.
 #include "common.cuh"
+#include "kernels.cuh"
 #include "ptx.cuh"
+
+#include <stdlib.h>
 
 namespace apla {
 
@@ -453,9 +456,13 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
 
 }  // namespace
 
-int attn_fwd(const void* qkv, void* out, float* lse, const int* cu_seqlens, int num_seqs, int max_seqlen, int H,
+int attn_fwd(const void* qkv, void* out, float* lse, const int* cu_seqlens, int num_seqs, int max_seqlen,
+             int total_tokens, int H,
              float scale, cudaStream_t stream) {
   APLA_CHECK(num_seqs > 0 && max_seqlen > 0 && H > 0, "attn_fwd: empty problem");
+  // default: tcgen05/TMEM kernel (attention_tc.cu); APLA_ATTN_IMPL=0 selects the mma.sync kernel below (A/B checks)
+  static const int impl = [] { const char* e = getenv("APLA_ATTN_IMPL"); return e ? atoi(e) : 1; }();
+  if (impl != 0) return attn_fwd_tc(qkv, out, lse, cu_seqlens, num_seqs, max_seqlen, total_tokens, H, scale, stream);
   dim3 grid(cdiv(max_seqlen, TS), num_seqs * H);
   attn_fwd_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
                                             reinterpret_cast<__nv_bfloat16*>(out), lse, cu_seqlens, max_seqlen, H, scale);
@@ -473,6 +480,9 @@ int attn_bwd(const void* qkv, const void* out, const void* dout, const float* ls
       reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(out), delta, n_chunks);
   APLA_CUDA(cudaGetLastError());
   count_launch();
+  static const int impl = [] { const char* e = getenv("APLA_ATTN_IMPL"); return e ? atoi(e) : 1; }();
+  if (impl != 0)
+    return attn_bwd_tc(qkv, dout, lse, delta, dqkv, cu_seqlens, num_seqs, max_seqlen, total_tokens, H, scale, stream);
   dim3 grid(cdiv(max_seqlen, TS), num_seqs * H);
   attn_bwd_dkdv_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                  reinterpret_cast<const __nv_bfloat16*>(dout), lse, delta,

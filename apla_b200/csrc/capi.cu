@@ -70,8 +70,9 @@ int apla_gather_cols(const void* dy, int64_t ld, void* sub, int64_t ld_sub, cons
 }
 
 int apla_attn_fwd(const void* qkv, void* out, float* lse, const int32_t* cu_seqlens, int num_seqs, int max_seqlen,
+                  int total_tokens,
                   int H, float scale, apla_stream_t stream) {
-  return attn_fwd(qkv, out, lse, cu_seqlens, num_seqs, max_seqlen, H, scale, S(stream));
+  return attn_fwd(qkv, out, lse, cu_seqlens, num_seqs, max_seqlen, total_tokens, H, scale, S(stream));
 }
 int apla_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
                   const int32_t* cu_seqlens, int num_seqs, int max_seqlen, int total_tokens, int H, float scale,

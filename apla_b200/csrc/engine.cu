@@ -116,7 +116,7 @@ static int engine_forward(Engine* e, const float* images, const int64_t* labels,
     if (int rc = layernorm_fwd(x_in, D, b.ln1w, b.ln1b, ln_out, D, T, D, e->eps, s)) return rc;
     if (int rc = gemm_tn(EPI_BIAS, ln_out, b.wqkv, T, 3 * D, D, D, D, b.qkv, nullptr, b.bqkv, nullptr, nullptr, 3 * D, s, 0))
       return rc;
-    if (int rc = attn_fwd(b.qkv, b.ao, b.lse, nullptr, B, N, e->H, e->scale, s)) return rc;
+    if (int rc = attn_fwd(b.qkv, b.ao, b.lse, nullptr, B, N, T, e->H, e->scale, s)) return rc;
     if (int rc = gemm_tn(EPI_RESID, b.ao, b.wproj, T, D, D, D, D, x_mid, nullptr, b.bproj, b.g1, x_in, D, s, 0)) return rc;
     if (int rc = layernorm_fwd(x_mid, D, b.ln2w, b.ln2b, ln_out, D, T, D, e->eps, s)) return rc;
     if (int rc = gemm_tn(EPI_BIAS_GELU, ln_out, b.wfc1, T, Hd, D, D, D, b.hpre, gelu_out, b.bfc1, nullptr, nullptr, Hd, s, 0))

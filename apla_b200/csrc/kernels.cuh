@@ -16,8 +16,14 @@ int gemm_wgrad_nt(const void* A, const void* B, int M, int N, int K, int lda, in
                   const int* rowmap, int n_valid, cudaStream_t stream);
 
 // attention.cu
-int attn_fwd(const void* qkv, void* out, float* lse, const int* cu_seqlens, int num_seqs, int max_seqlen, int H,
+int attn_fwd(const void* qkv, void* out, float* lse, const int* cu_seqlens, int num_seqs, int max_seqlen,
+             int total_tokens, int H,
              float scale, cudaStream_t stream);
+int attn_fwd_tc(const void* qkv, void* out, float* lse, const int* cu_seqlens, int num_seqs, int max_seqlen,
+                int total_tokens, int H, float scale, cudaStream_t stream);
+int attn_bwd_tc(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
+                const int* cu_seqlens, int num_seqs, int max_seqlen, int total_tokens, int H, float scale,
+                cudaStream_t stream);
 int attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
              const int* cu_seqlens, int num_seqs, int max_seqlen, int total_tokens, int H, float scale,
              cudaStream_t stream);

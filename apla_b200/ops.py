@@ -147,7 +147,7 @@ def attn_fwd(qkv, H: int, scale: float, num_seqs: int, max_seqlen: int, cu_seqle
         out = torch.empty(T, H * 64, device=qkv.device, dtype=BF16)
     if lse is None:
         lse = torch.empty(T, H, device=qkv.device, dtype=F32)
-    LIB.call("apla_attn_fwd", ptr(qkv), ptr(out), ptr(lse), ptr(cu_seqlens), num_seqs, max_seqlen, H, scale, stream())
+    LIB.call("apla_attn_fwd", ptr(qkv), ptr(out), ptr(lse), ptr(cu_seqlens), num_seqs, max_seqlen, T, H, scale, stream())
     return out, lse
 
 

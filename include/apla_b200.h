@@ -83,6 +83,7 @@ int apla_gather_cols(const void* dy, int64_t ld, void* sub, int64_t ld_sub, cons
  * sequences of max_seqlen tokens (appla_attn.py:56-60); otherwise int32[num_seqs+1] packed offsets = the
  * BlockDiagonalMask of appla_attn_mem_eff.py:37-43 / dinov2/layers/block.py:191-217. */
 int apla_attn_fwd(const void* qkv, void* out, float* lse, const int32_t* cu_seqlens, int num_seqs, int max_seqlen,
+                  int total_tokens,
                   int H, float scale, apla_stream_t stream);
 /* dqkv_bf16[T, 3*H*64] from dout_bf16[T, H*64]; delta_f32[T, H] is workspace. */
 int apla_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
