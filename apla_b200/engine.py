@@ -300,12 +300,63 @@ class FineTuneEngine:
         self.optim_step()
         return self.loss
 
-    def step_from_host(self, images_pinned: torch.Tensor, labels_pinned: torch.Tensor) -> float:
-        """The end-to-end call: pinned host batch -> H2D -> step -> loss read back to the host."""
-        self.images_dev.copy_(images_pinned, non_blocking=True)
-        self.labels_dev.copy_(labels_pinned, non_blocking=True)
-        loss = self.step(self.images_dev, self.labels_dev)
-        return float(loss.item())
+    def step_from_host(self, images_pinned: torch.Tensor, labels_pinned: torch.Tensor, lag: bool = True):
+        """The end-to-end call: pinned host batch -> H2D -> step -> loss read back to the host.
+
+        The batch is copied on a side stream into one of two device slots (so the copy of step k overlaps the compute
+        of step k-1) and the loss comes back through a pinned buffer.  With `lag=True` (default) the call returns the
+        loss of the PREVIOUS step (None on the first call) so that the host never waits for the step it just enqueued
+        -- the same one-step-late logging the reference does every `log_every` (src/defaults/trainer.py:145-151);
+        `lag=False` synchronises and returns this step's loss.  `drain()` returns the last pending loss."""
+        if not hasattr(self, "_e2e"):
+            B, img = self.shape["B"], self.shape["img"]
+            self._e2e = dict(
+                copy_stream=torch.cuda.Stream(device=self.device),
+                img=[self.images_dev, self._new(B, 3, img, img, dtype=F32)],
+                lab=[self.labels_dev, self._new(B, dtype=torch.int64)],
+                copied=[torch.cuda.Event(), torch.cuda.Event()],
+                done=[torch.cuda.Event(), torch.cuda.Event()],
+                loss_host=[torch.zeros(1, dtype=F32).pin_memory(), torch.zeros(1, dtype=F32).pin_memory()],
+                pending=[False, False], slot=0)
+        st = self._e2e
+        slot = st["slot"]
+        st["slot"] = slot ^ 1
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(st["copy_stream"]):
+            if st["pending"][slot]:
+                st["copy_stream"].wait_event(st["done"][slot])      # the step that last read this slot has finished
+            st["img"][slot].copy_(images_pinned, non_blocking=True)
+            st["lab"][slot].copy_(labels_pinned, non_blocking=True)
+            st["copied"][slot].record()
+        cur.wait_event(st["copied"][slot])
+        self.step(st["img"][slot], st["lab"][slot])
+        st["loss_host"][slot].copy_(self.loss, non_blocking=True)
+        st["done"][slot].record(cur)
+        st["pending"][slot] = True
+        if lag:
+            # this step is enqueued; only now wait for the previous one, so the GPU always has a step queued
+            prev = slot ^ 1
+            prev_loss = None
+            if st["pending"][prev]:
+                st["done"][prev].synchronize()
+                prev_loss = float(st["loss_host"][prev][0])
+                st["pending"][prev] = False
+            return prev_loss
+        st["done"][slot].synchronize()
+        st["pending"][slot] = False
+        return float(st["loss_host"][slot][0])
+
+    def drain(self):
+        """Wait for the last enqueued step_from_host() and return its loss (None if nothing is pending)."""
+        st = getattr(self, "_e2e", None)
+        if st is None:
+            return None
+        last = st["slot"] ^ 1
+        if not st["pending"][last]:
+            return None
+        st["done"][last].synchronize()
+        st["pending"][last] = False
+        return float(st["loss_host"][last][0])
 
     def grad_norm(self) -> torch.Tensor:
         """sqrt of the sum of squares the last optim_step clipped with (after the 1/world scaling)."""

@@ -232,7 +232,9 @@ def run_gpu(args):
     ms_step = timed(lambda: eng.step(images_dev, labels_dev), args.steps, max(0, args.warmup - 1))
     clocks = sampler.stop() if sampler else None
     ms_e2e = timed(lambda: eng.step_from_host(images_pin, labels_pin), args.steps, max(1, args.warmup // 2))
-    loss = float(eng.loss.item())
+    loss = eng.drain()
+    if loss is None:
+        loss = float(eng.loss.item())
 
     if rank == 0:
         peaks = load_peaks()
