@@ -480,7 +480,11 @@ int attn_bwd(const void* qkv, const void* out, const void* dout, const float* ls
       reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(out), delta, n_chunks);
   APLA_CUDA(cudaGetLastError());
   count_launch();
-  static const int impl = [] { const char* e = getenv("APLA_ATTN_IMPL"); return e ? atoi(e) : 1; }();
+  // default (2): sequence-resident pipelined tcgen05 kernels for short sequences (attention_sr.cu), streaming
+  // tcgen05 kernels (attention_tc_bwd.cu) otherwise; APLA_ATTN_IMPL=1 forces the streaming kernels, 0 mma.sync
+  static const int impl = [] { const char* e = getenv("APLA_ATTN_IMPL"); return e ? atoi(e) : 2; }();
+  if (impl >= 2 && attn_sr_supported(max_seqlen))
+    return attn_bwd_sr(qkv, dout, lse, delta, dqkv, cu_seqlens, num_seqs, max_seqlen, total_tokens, H, scale, stream);
   if (impl != 0)
     return attn_bwd_tc(qkv, dout, lse, delta, dqkv, cu_seqlens, num_seqs, max_seqlen, total_tokens, H, scale, stream);
   dim3 grid(cdiv(max_seqlen, TS), num_seqs * H);

@@ -24,6 +24,11 @@ int attn_fwd_tc(const void* qkv, void* out, float* lse, const int* cu_seqlens, i
 int attn_bwd_tc(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
                 const int* cu_seqlens, int num_seqs, int max_seqlen, int total_tokens, int H, float scale,
                 cudaStream_t stream);
+// attention_sr.cu: whole-sequence-resident pipelined kernels (max_seqlen <= 272)
+bool attn_sr_supported(int max_seqlen);
+int attn_bwd_sr(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
+                const int* cu_seqlens, int num_seqs, int max_seqlen, int total_tokens, int H, float scale,
+                cudaStream_t stream);
 int attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
              const int* cu_seqlens, int num_seqs, int max_seqlen, int total_tokens, int H, float scale,
              cudaStream_t stream);
