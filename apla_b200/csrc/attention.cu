@@ -482,7 +482,9 @@ int attn_bwd(const void* qkv, const void* out, const void* dout, const float* ls
   count_launch();
   // default (2): sequence-resident pipelined tcgen05 kernels for short sequences (attention_sr.cu), streaming
   // tcgen05 kernels (attention_tc_bwd.cu) otherwise; APLA_ATTN_IMPL=1 forces the streaming kernels, 0 mma.sync
-  static const int impl = [] { const char* e = getenv("APLA_ATTN_IMPL"); return e ? atoi(e) : 2; }();
+  static const int impl = [] { const char* e = getenv("APLA_ATTN_IMPL"); return e ? atoi(e) : 3; }();
+  if (impl >= 3 && attn_fused_supported(max_seqlen))
+    return attn_bwd_fused(qkv, dout, lse, delta, dqkv, cu_seqlens, num_seqs, max_seqlen, total_tokens, H, scale, stream);
   if (impl >= 2 && attn_sr_supported(max_seqlen))
     return attn_bwd_sr(qkv, dout, lse, delta, dqkv, cu_seqlens, num_seqs, max_seqlen, total_tokens, H, scale, stream);
   if (impl != 0)
