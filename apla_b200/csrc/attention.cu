@@ -461,7 +461,9 @@ int attn_fwd(const void* qkv, void* out, float* lse, const int* cu_seqlens, int 
              float scale, cudaStream_t stream) {
   APLA_CHECK(num_seqs > 0 && max_seqlen > 0 && H > 0, "attn_fwd: empty problem");
   // default: tcgen05/TMEM kernel (attention_tc.cu); APLA_ATTN_IMPL=0 selects the mma.sync kernel below (A/B checks)
-  static const int impl = [] { const char* e = getenv("APLA_ATTN_IMPL"); return e ? atoi(e) : 1; }();
+  static const int impl = [] { const char* e = getenv("APLA_ATTN_IMPL"); return e ? atoi(e) : 3; }();
+  if (impl >= 3 && attn_fused_supported(max_seqlen))
+    return attn_fwd_sr(qkv, out, lse, cu_seqlens, num_seqs, max_seqlen, total_tokens, H, scale, stream);
   if (impl != 0) return attn_fwd_tc(qkv, out, lse, cu_seqlens, num_seqs, max_seqlen, total_tokens, H, scale, stream);
   dim3 grid(cdiv(max_seqlen, TS), num_seqs * H);
   attn_fwd_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),

@@ -29,6 +29,9 @@ bool attn_sr_supported(int max_seqlen);
 int attn_bwd_sr(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
                 const int* cu_seqlens, int num_seqs, int max_seqlen, int total_tokens, int H, float scale,
                 cudaStream_t stream);
+// attention_fwd_sr.cu: persistent sequence-resident forward, max_seqlen <= 272
+int attn_fwd_sr(const void* qkv, void* out, float* lse, const int* cu_seqlens, int num_seqs, int max_seqlen,
+                int total_tokens, int H, float scale, cudaStream_t stream);
 // attention_fused.cu: single-pass fused backward (dQ, dK, dV in one launch), max_seqlen <= 272
 bool attn_fused_supported(int max_seqlen);
 int attn_bwd_fused(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,

@@ -29,7 +29,7 @@ __device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a_t, uint32_t b_lo,
 
 // mode 0: SS, A K-major / B K-major   1: TS, B K-major   2: SS, A K-major / B MN-major   3: TS, B MN-major
 // 4: SS, A MN-major (M=128 = two boxes 16 KB apart) / B MN-major
-__global__ void __launch_bounds__(128, 1) bench(int mode, int N, int iters, long long* out) {
+__global__ void __launch_bounds__(128, 1) bench(int mode, int N, int iters, int nacc, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
@@ -60,9 +60,12 @@ __global__ void __launch_bounds__(128, 1) bench(int mode, int N, int iters, long
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const uint32_t bd = b_mn ? DESC_LO_MN + b_lo + kk * 128 : DESC_LO_K + b_lo + 2 * kk;
-          if (mode == 0 || mode == 2) umma_ss(tmem, DESC_LO_K + a_lo + 2 * kk, bd, idesc, 1);
-          else if (mode == 4) umma_ss(tmem, DESC_LO_MN + a_lo + kk * 128, bd, idesc, 1);
-          else umma_ts(tmem, tmem + 256 + kk * 8, bd, idesc, 1);
+          // nacc independent accumulators used round-robin: separates per-instruction cost from the latency of a
+          // dependent accumulation chain
+          const uint32_t d = tmem + (nacc == 1 ? 0 : ((it * 4 + kk) & (nacc - 1)) * 64);
+          if (mode == 0 || mode == 2) umma_ss(d, DESC_LO_K + a_lo + 2 * kk, bd, idesc, 1);
+          else if (mode == 4) umma_ss(d, DESC_LO_MN + a_lo + kk * 128, bd, idesc, 1);
+          else umma_ts(d, tmem + 256 + kk * 8, bd, idesc, 1);
         }
       }
       umma_commit(&bar);
@@ -80,6 +83,58 @@ __global__ void __launch_bounds__(128, 1) bench(int mode, int N, int iters, long
   }
 }
 
+// nw issuer warps (one per SM sub-partition), each with its own accumulator and commit barrier: is the per-instruction
+// cost a property of the issuing thread or of the tensor pipe?
+__global__ void __launch_bounds__(128, 1) bench_multi(int mode, int N, int iters, int nw, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar[4];
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc<1>(&slot, 512);
+    tmem_relinquish<1>();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  const long long t0 = clock64();
+  if (warp < nw) {
+    const bool leader = elect_one();
+    const uint32_t a_lo = (smem_u32(smem) >> 4) + warp * 1024, b_lo = (smem_u32(smem + 64 * 1024) >> 4) + warp * 1024;
+    const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+    const uint32_t d = tmem + warp * 64;
+    if (leader) {
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if (mode == 0) umma_ss(d, DESC_LO_K + a_lo + 2 * kk, DESC_LO_K + b_lo + 2 * kk, idesc, 1);
+          else umma_ts(d, tmem + 256 + warp * 32 + kk * 8, DESC_LO_K + b_lo + 2 * kk, idesc, 1);
+        }
+      }
+      umma_commit(&bar[warp]);
+    }
+    __syncwarp();
+    mbar_wait(&bar[warp], 0);
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem, 512);
+  }
+}
+
 int main() {
   long long* d;
   cudaMalloc(&d, 8);
@@ -89,9 +144,10 @@ int main() {
                          "SS  A=MN-major B=MN-major"};
   const int iters = 2000;
   for (int mode = 0; mode < 5; ++mode) {
-    for (int N : {16, 32, 64, 128, 256}) {
+    for (int N : {16, 64, 128, 256}) for (int nacc : {1, 2, 4}) {
       if (mode >= 2 && N > 64) continue;   // MN-major B wider than one 64-element box is not laid out in this test
-      bench<<<148, 128, smem>>>(mode, N, iters, d);
+      if (nacc > 1 && N > 64) continue;
+      bench<<<148, 128, smem>>>(mode, N, iters, nacc, d);
       long long c = 0;
       cudaError_t e = cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
       if (e != cudaSuccess) {
@@ -99,9 +155,23 @@ int main() {
         return 1;
       }
       const double per = double(c) / (iters * 4);
-      printf("%s N=%3d: %7.1f cycles per MMA (floor %5.1f)  %6.1f B/clk smem\n", names[mode], N, per, 128.0 * N / 256,
+      printf("%s N=%3d acc=%d: %7.1f cycles per MMA (floor %5.1f)  %6.1f B/clk smem\n", names[mode], N, nacc, per, 128.0 * N / 256,
              ((mode == 1 || mode == 3 ? 0 : 4096) + 32.0 * N) / per);
     }
   }
+  cudaFuncSetAttribute(bench_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int mode = 0; mode < 2; ++mode)
+    for (int N : {16, 64, 128})
+      for (int nw : {1, 2, 4}) {
+        bench_multi<<<148, 128, smem>>>(mode, N, iters, nw, d);
+        long long c = 0;
+        cudaError_t e = cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+          printf("multi: %s\n", cudaGetErrorString(e));
+          return 1;
+        }
+        printf("%s N=%3d, %d issuer warps: %7.1f cycles per MMA (aggregate)\n", mode ? "TS" : "SS", N, nw,
+               double(c) / (iters * 4 * nw));
+      }
   return 0;
 }
