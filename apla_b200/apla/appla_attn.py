@@ -79,8 +79,9 @@ class _AplaAttentionFn(torch.autograd.Function):
                 ops.proj_wgrad(sub, ao, dw1, r)
                 ops.colsum(sub, db1, r)
         if ctx.needs_input_grad[0]:
-            d_ao = ops.gemm_dgrad(dyb, ws["wprojT"])
-            dqkv = ops.attn_bwd(qkv, ao, d_ao, lse, mod.num_heads, float(mod.scale), num_seqs, max_len, cu_seqlens=cu)
+            d_ao, delta = ops.gemm_dgrad_delta(dyb, ws["wprojT"], ao)
+            dqkv = ops.attn_bwd(qkv, None, d_ao, lse, mod.num_heads, float(mod.scale), num_seqs, max_len,
+                                cu_seqlens=cu, delta=delta)
             dx = ops.gemm_dgrad(dqkv, ws["wqkvT"]).view(ctx.x_shape).to(ctx.x_dtype)
         return dx, dw1, db1, None, None, None
 

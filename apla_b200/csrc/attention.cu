@@ -477,11 +477,14 @@ int attn_bwd(const void* qkv, const void* out, const void* dout, const float* ls
              const int* cu_seqlens, int num_seqs, int max_seqlen, int total_tokens, int H, float scale,
              cudaStream_t stream) {
   APLA_CHECK(num_seqs > 0 && max_seqlen > 0 && H > 0, "attn_bwd: empty problem");
-  const size_t n_chunks = size_t(total_tokens) * H * 8;
-  attn_delta_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(out), delta, n_chunks);
-  APLA_CUDA(cudaGetLastError());
-  count_launch();
+  // out == nullptr: delta = rowsum(dO * O) was already produced by the projection-dgrad GEMM epilogue (EPI_DELTA)
+  if (out != nullptr) {
+    const size_t n_chunks = size_t(total_tokens) * H * 8;
+    attn_delta_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(out), delta, n_chunks);
+    APLA_CUDA(cudaGetLastError());
+    count_launch();
+  }
   // default (2): sequence-resident pipelined tcgen05 kernels for short sequences (attention_sr.cu), streaming
   // tcgen05 kernels (attention_tc_bwd.cu) otherwise; APLA_ATTN_IMPL=1 forces the streaming kernels, 0 mma.sync
   static const int impl = [] { const char* e = getenv("APLA_ATTN_IMPL"); return e ? atoi(e) : 3; }();

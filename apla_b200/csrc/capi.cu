@@ -44,6 +44,10 @@ int apla_gemm_dgrad_gelu_bwd(const void* dY, int ldy, const void* Wt, int ldwt, 
                              int M, int K_in, int N_out, apla_stream_t stream) {
   return gemm_tn(EPI_GELU_BWD, dY, Wt, M, K_in, N_out, ldy, ldwt, dH, nullptr, nullptr, nullptr, h, ldh, S(stream), 0);
 }
+int apla_gemm_dgrad_delta(const void* dY, int ldy, const void* Wt, int ldwt, const void* O, void* dO, int ldo,
+                          float* delta, int M, int D, int N_out, apla_stream_t stream) {
+  return gemm_tn(EPI_DELTA, dY, Wt, M, D, N_out, ldy, ldwt, dO, delta, nullptr, nullptr, O, ldo, S(stream), 0);
+}
 int apla_proj_wgrad_gather(const void* dYsub, int ldy, const void* X, int ldx, const int32_t* rowmap, float* dW1,
                            int ldw, int T, int D_in, int n_pad, int r, apla_stream_t stream) {
   // dW1^T[D_in, n] = X^T[D_in, T] . dYsub[T, n]: D_in on the MMA M dimension, the (small) r on N

@@ -198,8 +198,10 @@ static int engine_backward(Engine* e, int l_from, int l_to, cudaStream_t s) {
     }
     if (l == 0) break;  // nothing trainable upstream of block 0's attention
     void* dO = e->get<void>("dO");
-    if (int rc = gemm_tn(EPI_BIAS, dxb, b.wprojT, T, D, D, D, D, dO, nullptr, nullptr, nullptr, nullptr, D, s, 0)) return rc;
-    if (int rc = attn_bwd(b.qkv, b.ao, dO, b.lse, e->get<float>("delta"), e->get<void>("dqkv"), nullptr, B, N, T, e->H,
+    // dO = dY Wproj, and delta = rowsum(dO * O) per (token, head) from the same epilogue
+    if (int rc = gemm_tn(EPI_DELTA, dxb, b.wprojT, T, D, D, D, D, dO, e->get<float>("delta"), nullptr, nullptr, b.ao, D, s, 0))
+      return rc;
+    if (int rc = attn_bwd(b.qkv, nullptr, dO, b.lse, e->get<float>("delta"), e->get<void>("dqkv"), nullptr, B, N, T, e->H,
                           e->scale, s))
       return rc;
     if (int rc = gemm_tn(EPI_BIAS, e->get<void>("dqkv"), b.wqkvT, T, D, 3 * D, 3 * D, 3 * D, dln, nullptr, nullptr, nullptr,

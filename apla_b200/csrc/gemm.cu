@@ -360,7 +360,14 @@ int gemm_tn(int epi, const void* A, const void* B, int M, int N, int K, int lda,
              ldb);
   APLA_CHECK(ldo % 8 == 0, "gemm_tn: ldo=%d must be a multiple of 8", ldo);
   APLA_CHECK(epi != EPI_BIAS_GELU || out2 != nullptr, "gemm_tn: EPI_BIAS_GELU needs out2");
-  APLA_CHECK((epi != EPI_RESID && epi != EPI_GELU_BWD) || aux != nullptr, "gemm_tn: this epilogue needs aux");
+  APLA_CHECK((epi != EPI_RESID && epi != EPI_GELU_BWD && epi != EPI_DELTA) || aux != nullptr,
+             "gemm_tn: this epilogue needs aux");
+  if (epi == EPI_DELTA) {
+    APLA_CHECK(out2 != nullptr && N % 64 == 0, "gemm_tn: EPI_DELTA needs the delta buffer in out2 and N %% 64 == 0");
+    int bn = bn_override;
+    if (bn <= 0) { const char* e = getenv("APLA_GEMM_BN"); bn = e ? atoi(e) : 0; }
+    return gemm2_tn(epi, A, B, M, N, K, lda, ldb, out, out2, bias, gamma, aux, ldo, stream, bn);
+  }
   {
     // default: the 2-CTA kernel with TMA-store epilogues (gemm2.cu); APLA_GEMM_IMPL=1 selects the 1-CTA kernel below
     // (kept for A/B measurements and as the weight-gradient kernel).

@@ -11,7 +11,10 @@
 //               saved pre-activation) arrive by TMA load one chunk ahead, results leave by TMA store, so global
 //               memory only ever sees full 128-byte rows (the first version of this kernel wrote registers straight
 //               to global memory, 32 rows per instruction, and was LSU-wavefront-bound in every fused epilogue).
-// Epilogues: see kernels.cuh / gemm.cu header (EPI_BIAS, EPI_BIAS_GELU, EPI_RESID, EPI_GELU_BWD).
+// Epilogues: see kernels.cuh / gemm.cu header (EPI_BIAS, EPI_BIAS_GELU, EPI_RESID, EPI_GELU_BWD), plus
+//   EPI_DELTA  out_bf16 = acc;  rowstat[m, n/64] = sum over the 64-wide head of bf16(acc) * aux_bf16[m, n]
+//              (attention-projection dgrad fused with FlashAttention's delta = rowsum(dO * O); one staging chunk is
+//              exactly one head and one thread owns one row of it, so the reduction needs no shuffles).
 #include "common.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -60,7 +63,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
              const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_out2,
              const __grid_constant__ CUtensorMap tma_aux, int M, int N, int K, const float* __restrict__ bias,
-             const float* __restrict__ gamma) {
+             const float* __restrict__ gamma, float* __restrict__ rowstat) {
   using C = Cfg<BN>;
   constexpr int kStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -88,7 +91,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     tma_prefetch_desc(&tma_b);
     tma_prefetch_desc(&tma_out);
     if constexpr (EPI == EPI_BIAS_GELU) tma_prefetch_desc(&tma_out2);
-    if constexpr (EPI == EPI_RESID || EPI == EPI_GELU_BWD) tma_prefetch_desc(&tma_aux);
+    if constexpr (EPI == EPI_RESID || EPI == EPI_GELU_BWD || EPI == EPI_DELTA) tma_prefetch_desc(&tma_aux);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -163,7 +166,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
   } else {
     // ===================== epilogue warps (both CTAs) =====================
     constexpr bool kF32 = (EPI == EPI_RESID);
-    constexpr bool kAux = (EPI == EPI_RESID || EPI == EPI_GELU_BWD);
+    constexpr bool kAux = (EPI == EPI_RESID || EPI == EPI_GELU_BWD || EPI == EPI_DELTA);
     // columns per chunk: one 128-byte staging row, except the two-output GELU epilogue which packs a 64-byte row of
     // each output (h | g) into one 4 KB buffer (64B swizzle) so that chunks can still ping-pong between buffers
     constexpr int CW = (kF32 || EPI == EPI_BIAS_GELU) ? 32 : 64;
@@ -216,6 +219,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             __syncwarp();
           }
           const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + cidx * CW);
+          [[maybe_unused]] float dot = 0.f;  // EPI_DELTA: this row's sum over the chunk (= one 64-wide head)
 #pragma unroll
           for (int s = 0; s < CW / 32; ++s) {
             uint32_t v[32];
@@ -225,7 +229,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
             const int col = col0 + s * 32;
-            if constexpr (EPI != EPI_GELU_BWD) {
+            if constexpr (EPI != EPI_GELU_BWD && EPI != EPI_DELTA) {
               if (bias) {
                 const float4* b4 = reinterpret_cast<const float4*>(bias + col);
 #pragma unroll
@@ -278,7 +282,25 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                                    x[8 * c + 2 * t + 1] * gelu_erf_grad(bf16_hi(hw[t])));
                 sts128(a, d[0], d[1], d[2], d[3]);
               }
+            } else if constexpr (EPI == EPI_DELTA) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint32_t a = stg_addr(buf, lane, 4 * s + c);
+                const uint4 ov = lds128(a);
+                const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w};
+                uint32_t d[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  d[t] = pack_bf16(x[8 * c + 2 * t], x[8 * c + 2 * t + 1]);
+                  dot = fmaf(bf16_lo(d[t]), bf16_lo(ow[t]), dot);   // the rounded dO the attention backward will read
+                  dot = fmaf(bf16_hi(d[t]), bf16_hi(ow[t]), dot);
+                }
+                sts128(a, d[0], d[1], d[2], d[3]);
+              }
             }
+          }
+          if constexpr (EPI == EPI_DELTA) {
+            if (row0 + lane < M) rowstat[size_t(row0 + lane) * (N >> 6) + (col0 >> 6)] = dot;
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -314,6 +336,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
 template <int BN, int EPI>
 static int launch(const void* A, const void* B, int M, int N, int K, int lda, int ldb, void* out, void* out2,
                   const float* bias, const float* gamma, const void* aux, int ldo, cudaStream_t stream) {
+  float* rowstat = EPI == EPI_DELTA ? reinterpret_cast<float*>(out2) : nullptr;
   using C = Cfg<BN>;
   CUtensorMap ta, tb, to, to2, tx;
   if (int rc = make_tmap_2d(&ta, A, 2, M, K, lda, BM, BK, true)) return rc;
@@ -327,7 +350,7 @@ static int launch(const void* A, const void* B, int M, int N, int K, int lda, in
     to2 = to;
   }
   tx = to;
-  if (EPI == EPI_RESID || EPI == EPI_GELU_BWD)
+  if (EPI == EPI_RESID || EPI == EPI_GELU_BWD || EPI == EPI_DELTA)
     if (int rc = make_tmap_2d(&tx, aux, oelt, M, N, ldo, 32, 128 / oelt, true)) return rc;
   auto kern = gemm2_kernel<BN, EPI>;
   static bool attr_set = false;
@@ -338,7 +361,7 @@ static int launch(const void* A, const void* B, int M, int N, int K, int lda, in
   const int tiles = cdiv(M, 2 * BM) * cdiv(N, BN);
   const int max_clusters = sm_count() / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  kern<<<2 * clusters, kThreads, C::kSmemBytes, stream>>>(ta, tb, to, to2, tx, M, N, K, bias, gamma);
+  kern<<<2 * clusters, kThreads, C::kSmemBytes, stream>>>(ta, tb, to, to2, tx, M, N, K, bias, gamma, rowstat);
   APLA_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -371,6 +394,8 @@ int gemm2_tn(int epi, const void* A, const void* B, int M, int N, int K, int lda
     case EPI_RESID: return g2::dispatch<EPI_RESID>(A, B, M, N, K, lda, ldb, out, out2, bias, gamma, aux, ldo, stream, bn);
     case EPI_GELU_BWD:
       return g2::dispatch<EPI_GELU_BWD>(A, B, M, N, K, lda, ldb, out, out2, bias, gamma, aux, ldo, stream, bn);
+    case EPI_DELTA:
+      return g2::dispatch<EPI_DELTA>(A, B, M, N, K, lda, ldb, out, out2, bias, gamma, aux, ldo, stream, bn);
   }
   set_error("gemm2_tn: unknown epilogue %d", epi);
   return 1;

@@ -76,6 +76,23 @@ def gemm_dgrad(dy, wt, out=None):
     return out
 
 
+def gemm_dgrad_delta(dy, wt, o, out=None, delta=None):
+    """dO[M,D] = dy @ wt^T and delta[M, D/64] = per-head rowsum(dO * o): projection dgrad + attention-backward delta."""
+    require_device()
+    _chk(dy, BF16, "dy", 2); _chk(wt, BF16, "wt", 2); _chk(o, BF16, "o", 2)
+    M, Nout = dy.shape; D = wt.shape[0]
+    if D % 64 != 0 or tuple(o.shape) != (M, D):
+        raise RuntimeError(f"o must be [{M},{D}] with D a multiple of 64, got {tuple(o.shape)}")
+    if out is None:
+        out = torch.empty(M, D, device=dy.device, dtype=BF16)
+    if delta is None:
+        delta = torch.empty(M, D // 64, device=dy.device, dtype=F32)
+    assert _ld(out) == _ld(o) and delta.is_contiguous()
+    LIB.call("apla_gemm_dgrad_delta", ptr(dy), _ld(dy), ptr(wt), _ld(wt), ptr(o), ptr(out), _ld(out), ptr(delta), M, D,
+             Nout, stream())
+    return out, delta
+
+
 def gemm_dgrad_gelu_bwd(dy, wt, h, out=None):
     require_device()
     _chk(dy, BF16, "dy", 2); _chk(wt, BF16, "wt", 2); _chk(h, BF16, "h", 2)
@@ -154,9 +171,15 @@ def attn_fwd(qkv, H: int, scale: float, num_seqs: int, max_seqlen: int, cu_seqle
 def attn_bwd(qkv, out, dout, lse, H: int, scale: float, num_seqs: int, max_seqlen: int, cu_seqlens=None, dqkv=None,
              delta=None):
     require_device()
-    _chk(qkv, BF16, "qkv", 2); _chk(out, BF16, "out", 2); _chk(dout, BF16, "dout", 2); _chk(lse, F32, "lse", 2)
+    _chk(qkv, BF16, "qkv", 2); _chk(dout, BF16, "dout", 2); _chk(lse, F32, "lse", 2)
     T = qkv.shape[0]
-    assert dout.is_contiguous() and out.is_contiguous() and qkv.is_contiguous()
+    assert dout.is_contiguous() and qkv.is_contiguous()
+    if out is None:      # delta precomputed by gemm_dgrad_delta
+        if delta is None:
+            raise RuntimeError("attn_bwd: out=None needs the precomputed delta")
+    else:
+        _chk(out, BF16, "out", 2)
+        assert out.is_contiguous()
     if dqkv is None:
         dqkv = torch.empty_like(qkv)
     if delta is None:

@@ -52,6 +52,11 @@ int apla_gemm_dgrad(const void* dY, int ldy, const void* Wt, int ldwt, void* dX,
 /* dH_bf16 = (dY . Wt^T) * gelu_erf'(h_bf16): fc2 input gradient fused with GELU backward (vit.py:164-166). */
 int apla_gemm_dgrad_gelu_bwd(const void* dY, int ldy, const void* Wt, int ldwt, const void* h, void* dH, int ldh,
                              int M, int K_in, int N_out, apla_stream_t stream);
+/* dO_bf16[M,D] = dY_bf16[M,D_out] . Wt^T  and  delta_f32[M, D/64] = rowsum over each 64-wide head of dO * O_bf16:
+ * the input gradient of the attention projection (backward of appla_attn.py:64-79) fused with the softmax-backward
+ * row term of the attention that produced O (appla_attn.py:58-62); pass the result to apla_attn_bwd with out = NULL. */
+int apla_gemm_dgrad_delta(const void* dY, int ldy, const void* Wt, int ldwt, const void* O, void* dO, int ldo,
+                          float* delta, int M, int D, int N_out, apla_stream_t stream);
 /* APLA weight gradient.  dW1_f32[r, D_in] += dYsub^T . X  where dYsub_bf16[T, n_pad] holds the r gathered
  * output-gradient columns (n_pad = r rounded up to 64, zero padded) and X_bf16[T, D_in] is the projection input.
  * With rowmap != NULL, dYsub is the full [T, D_out] gradient and rowmap[n] (int32, -1 = frozen) is the
@@ -85,7 +90,8 @@ int apla_gather_cols(const void* dy, int64_t ld, void* sub, int64_t ld_sub, cons
 int apla_attn_fwd(const void* qkv, void* out, float* lse, const int32_t* cu_seqlens, int num_seqs, int max_seqlen,
                   int total_tokens,
                   int H, float scale, apla_stream_t stream);
-/* dqkv_bf16[T, 3*H*64] from dout_bf16[T, H*64]; delta_f32[T, H] is workspace. */
+/* dqkv_bf16[T, 3*H*64] from dout_bf16[T, H*64]; delta_f32[T, H] is workspace, or -- with out == NULL -- the
+ * precomputed rowsum(dout * out) per (token, head) from apla_gemm_dgrad_delta. */
 int apla_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
                   const int32_t* cu_seqlens, int num_seqs, int max_seqlen, int total_tokens, int H, float scale,
                   apla_stream_t stream);

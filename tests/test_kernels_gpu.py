@@ -103,6 +103,22 @@ def test_gemm_dgrad_and_gelu_bwd():
     assert rel(dh.float(), hh.grad) < 5e-3
 
 
+@pytest.mark.parametrize("M,D", [(514, 768), (1576, 384), (16448, 768)])
+def test_gemm_dgrad_delta(M, D):
+    """Projection dgrad with the fused delta = rowsum(dO * O) per (token, head) epilogue."""
+    ops = _cuda()
+    g = torch.Generator(device="cuda").manual_seed(M + D)
+    dy = bf(torch.randn(M, D, device="cuda", generator=g))
+    W = bf(torch.randn(D, D, device="cuda", generator=g) * 0.05)          # [out, in]
+    o = bf(torch.randn(M, D, device="cuda", generator=g))
+    d_o, delta = ops.gemm_dgrad_delta(dy, W.t().contiguous(), o)
+    ref = dy.float() @ W.float()
+    assert rel(d_o.float(), ref) < 4e-3
+    assert torch.equal(d_o, ops.gemm_dgrad(dy, W.t().contiguous()))       # same GEMM, bit-identical dO
+    dref = (d_o.float() * o.float()).view(M, D // 64, 64).sum(-1)          # delta of the ROUNDED dO
+    assert rel(delta, dref) < 1e-5
+
+
 @pytest.mark.parametrize("T,D,r", [(514, 768, 8), (1576, 384, 32), (2000, 768, 128), (16448, 768, 8)])
 def test_proj_wgrad_compact(T, D, r):
     ops = _cuda()
