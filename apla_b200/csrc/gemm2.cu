@@ -167,10 +167,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     // ===================== epilogue warps (both CTAs) =====================
     constexpr bool kF32 = (EPI == EPI_RESID);
     constexpr bool kAux = (EPI == EPI_RESID || EPI == EPI_GELU_BWD || EPI == EPI_DELTA);
+    constexpr bool kBias = (EPI != EPI_GELU_BWD && EPI != EPI_DELTA);
     // columns per chunk: one 128-byte staging row, except the two-output GELU epilogue which packs a 64-byte row of
     // each output (h | g) into one 4 KB buffer (64B swizzle) so that chunks can still ping-pong between buffers
     constexpr int CW = (kF32 || EPI == EPI_BIAS_GELU) ? 32 : 64;
     constexpr int NCH = BN / CW / 2;         // chunks per warp per tile
+    constexpr int SUBS = CW / 32;            // 32-column TMEM loads per chunk
+    constexpr int NSUB = NCH * SUBS;
     const int ew = warp - 2;
     const int q = warp & 3;                  // TMEM lane quarter of this warp
     const int half = ew >> 2;
@@ -183,10 +186,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int row0 = (tile / num_n) * (2 * BM) + int(cta_rank) * BM + q * 32;  // this warp's 32-row slab
       const int n0 = (tile % num_n) * BN;
-      const bool rows_ok = row0 < M;
+      // 32-column sub-loads of this warp that lie inside the matrix (warp-uniform; N % 32 == 0)
+      int nvalid = 0;
+      if (row0 < M) {
+#pragma unroll
+        for (int i = 0; i < NSUB; ++i) nvalid += (n0 + (half + 2 * (i / SUBS)) * CW + (i % SUBS) * 32 < N) ? 1 : 0;
+      }
       if constexpr (kAux) {
         // first chunk's auxiliary tile travels while the MMAs of this tile are still running
-        if (rows_ok && n0 + half * CW < N && lane == 0) {
+        if (nvalid > 0 && lane == 0) {
           const uint32_t b0 = cnt & 1;
           tma_store_wait_read<0>();
           mbar_arrive_expect_tx(&abar[b0], kStgBuf);
@@ -196,129 +204,161 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      if (rows_ok) {
-#pragma unroll 1
-        for (int j = 0; j < NCH; ++j) {
+      const uint32_t t_base = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + half * CW);
+      // The accumulator is read in a two-deep software pipeline: the tcgen05.ld (and the bias fetch) of sub-load
+      // i+1 is in flight while sub-load i goes through the epilogue math, and the TMEM stage goes back to the MMA
+      // thread as soon as the LAST sub-load has landed in registers -- not after the math and stores of the tile.
+      uint32_t v[2][32];
+      [[maybe_unused]] float4 bb[8];   // bias of the NEXT sub-load, fetched right after the current one is consumed
+      if (nvalid > 0) {
+        tmem_ld_32x32(t_base, v[0]);
+        if constexpr (kBias) {
+          if (bias) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bb[i] = __ldg(reinterpret_cast<const float4*>(bias + n0 + half * CW) + i);
+          }
+        }
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(&tempty[as], 0);
+      }
+      [[maybe_unused]] float dot = 0.f;  // EPI_DELTA: this row's sum over the chunk (= one 64-wide head)
+      int b = 0;
+      uint32_t buf = stg;
+#pragma unroll
+      for (int idx = 0; idx < NSUB; ++idx) {
+        if (idx < nvalid) {
+          const int j = idx / SUBS, s = idx % SUBS;
           const int cidx = half + 2 * j;
           const int col0 = n0 + cidx * CW;
-          if (col0 >= N) break;
-          const int b = int(cnt & 1);
-          ++cnt;
-          const uint32_t buf = stg + b * kStgBuf;
-          if constexpr (kAux) {
-            if (j + 1 < NCH && col0 + 2 * CW < N && lane == 0) {
-              tma_store_wait_read<0>();  // the other buffer's last store has drained
-              mbar_arrive_expect_tx(&abar[b ^ 1], kStgBuf);
-              tma_load_2d(reinterpret_cast<void*>(staging + ew * 2 * kStgBuf + (b ^ 1) * kStgBuf), &tma_aux,
-                          &abar[b ^ 1], col0 + 2 * CW, row0);
-            }
-            mbar_wait(&abar[b], (aux_phase >> b) & 1);
-            aux_phase ^= (1u << b);
-          } else {
-            if (lane == 0) tma_store_wait_read<1>();  // the store issued two chunks ago (same buffer) has drained
-            __syncwarp();
-          }
-          const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + cidx * CW);
-          [[maybe_unused]] float dot = 0.f;  // EPI_DELTA: this row's sum over the chunk (= one 64-wide head)
-#pragma unroll
-          for (int s = 0; s < CW / 32; ++s) {
-            uint32_t v[32];
-            tmem_ld_32x32(t_addr + s * 32, v);
-            tmem_ld_wait();
-            float x[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
-            const int col = col0 + s * 32;
-            if constexpr (EPI != EPI_GELU_BWD && EPI != EPI_DELTA) {
-              if (bias) {
-                const float4* b4 = reinterpret_cast<const float4*>(bias + col);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float4 bb = __ldg(b4 + i);
-                  x[4 * i] += bb.x; x[4 * i + 1] += bb.y; x[4 * i + 2] += bb.z; x[4 * i + 3] += bb.w;
-                }
+          if (s == 0) {
+            b = int(cnt & 1);
+            ++cnt;
+            buf = stg + b * kStgBuf;
+            if constexpr (kAux) {
+              if (j + 1 < NCH && col0 + 2 * CW < N && lane == 0) {
+                tma_store_wait_read<0>();  // the other buffer's last store has drained
+                mbar_arrive_expect_tx(&abar[b ^ 1], kStgBuf);
+                tma_load_2d(reinterpret_cast<void*>(staging + ew * 2 * kStgBuf + (b ^ 1) * kStgBuf), &tma_aux,
+                            &abar[b ^ 1], col0 + 2 * CW, row0);
               }
-            }
-            if constexpr (EPI == EPI_BIAS) {
-#pragma unroll
-              for (int c = 0; c < 4; ++c)
-                sts128(stg_addr(buf, lane, 4 * s + c), pack_bf16(x[8 * c], x[8 * c + 1]), pack_bf16(x[8 * c + 2], x[8 * c + 3]),
-                       pack_bf16(x[8 * c + 4], x[8 * c + 5]), pack_bf16(x[8 * c + 6], x[8 * c + 7]));
-            } else if constexpr (EPI == EPI_BIAS_GELU) {
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                uint32_t h[4], g[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                  h[t] = pack_bf16(x[8 * c + 2 * t], x[8 * c + 2 * t + 1]);
-                  g[t] = pack_bf16(gelu_erf(bf16_lo(h[t])), gelu_erf(bf16_hi(h[t])));
-                }
-                const uint32_t off = lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4);   // 64B-swizzled row of 32 bf16
-                sts128(buf + off, h[0], h[1], h[2], h[3]);
-                sts128(buf + kStgBuf / 2 + off, g[0], g[1], g[2], g[3]);
-              }
-            } else if constexpr (EPI == EPI_RESID) {
-              const float4* g4 = reinterpret_cast<const float4*>(gamma ? gamma + col : nullptr);
-#pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const uint32_t a = stg_addr(buf, lane, c);
-                const uint4 rv = lds128(a);
-                const float4 g = gamma ? __ldg(g4 + c) : make_float4(1.f, 1.f, 1.f, 1.f);
-                sts128(a, __float_as_uint(__uint_as_float(rv.x) + g.x * x[4 * c]),
-                       __float_as_uint(__uint_as_float(rv.y) + g.y * x[4 * c + 1]),
-                       __float_as_uint(__uint_as_float(rv.z) + g.z * x[4 * c + 2]),
-                       __float_as_uint(__uint_as_float(rv.w) + g.w * x[4 * c + 3]));
-              }
-            } else if constexpr (EPI == EPI_GELU_BWD) {
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const uint32_t a = stg_addr(buf, lane, 4 * s + c);
-                const uint4 hv = lds128(a);
-                const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
-                uint32_t d[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                  d[t] = pack_bf16(x[8 * c + 2 * t] * gelu_erf_grad(bf16_lo(hw[t])),
-                                   x[8 * c + 2 * t + 1] * gelu_erf_grad(bf16_hi(hw[t])));
-                sts128(a, d[0], d[1], d[2], d[3]);
-              }
-            } else if constexpr (EPI == EPI_DELTA) {
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const uint32_t a = stg_addr(buf, lane, 4 * s + c);
-                const uint4 ov = lds128(a);
-                const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w};
-                uint32_t d[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                  d[t] = pack_bf16(x[8 * c + 2 * t], x[8 * c + 2 * t + 1]);
-                  dot = fmaf(bf16_lo(d[t]), bf16_lo(ow[t]), dot);   // the rounded dO the attention backward will read
-                  dot = fmaf(bf16_hi(d[t]), bf16_hi(ow[t]), dot);
-                }
-                sts128(a, d[0], d[1], d[2], d[3]);
-              }
-            }
-          }
-          if constexpr (EPI == EPI_DELTA) {
-            if (row0 + lane < M) rowstat[size_t(row0 + lane) * (N >> 6) + (col0 >> 6)] = dot;
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            if constexpr (EPI == EPI_BIAS_GELU) {
-              const uint8_t* sb = staging + ew * 2 * kStgBuf + b * kStgBuf;
-              tma_store_2d(&tma_out, reinterpret_cast<const void*>(sb), col0, row0);
-              tma_store_2d(&tma_out2, reinterpret_cast<const void*>(sb + kStgBuf / 2), col0, row0);
+              mbar_wait(&abar[b], (aux_phase >> b) & 1);
+              aux_phase ^= (1u << b);
             } else {
-              tma_store_2d(&tma_out, reinterpret_cast<const void*>(staging + ew * 2 * kStgBuf + b * kStgBuf), col0, row0);
+              if (lane == 0) tma_store_wait_read<1>();  // the store issued two chunks ago (same buffer) has drained
+              __syncwarp();
             }
-            tma_store_commit();
+            dot = 0.f;
+          }
+          tmem_ld_wait_regs(v[idx & 1]);
+          if (idx + 1 < NSUB && idx + 1 < nvalid) {
+            const int j1 = (idx + 1) / SUBS, s1 = (idx + 1) % SUBS;
+            tmem_ld_32x32(t_base + uint32_t(2 * j1 * CW + s1 * 32), v[(idx + 1) & 1]);
+          }
+          if (idx + 1 == nvalid) {
+            // every tcgen05.ld of this tile has completed: hand the accumulator stage back to the leader's MMA thread
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_relaxed(&tempty[as], 0);
+          }
+          float x[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[idx & 1][i]);
+          const int col = col0 + s * 32;
+          if constexpr (kBias) {
+            if (bias) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 t4 = bb[i];
+                x[4 * i] += t4.x; x[4 * i + 1] += t4.y; x[4 * i + 2] += t4.z; x[4 * i + 3] += t4.w;
+              }
+              if (idx + 1 < NSUB && idx + 1 < nvalid) {
+                const int j1 = (idx + 1) / SUBS, s1 = (idx + 1) % SUBS;
+                const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + (half + 2 * j1) * CW + s1 * 32);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) bb[i] = __ldg(b4 + i);
+              }
+            }
+          }
+          if constexpr (EPI == EPI_BIAS) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              sts128(stg_addr(buf, lane, 4 * s + c), pack_bf16(x[8 * c], x[8 * c + 1]), pack_bf16(x[8 * c + 2], x[8 * c + 3]),
+                     pack_bf16(x[8 * c + 4], x[8 * c + 5]), pack_bf16(x[8 * c + 6], x[8 * c + 7]));
+          } else if constexpr (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t h[4], g[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                h[t] = pack_bf16(x[8 * c + 2 * t], x[8 * c + 2 * t + 1]);
+                g[t] = pack_bf16(gelu_erf(bf16_lo(h[t])), gelu_erf(bf16_hi(h[t])));
+              }
+              const uint32_t off = lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4);   // 64B-swizzled row of 32 bf16
+              sts128(buf + off, h[0], h[1], h[2], h[3]);
+              sts128(buf + kStgBuf / 2 + off, g[0], g[1], g[2], g[3]);
+            }
+          } else if constexpr (EPI == EPI_RESID) {
+            const float4* g4 = reinterpret_cast<const float4*>(gamma ? gamma + col : nullptr);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint32_t a = stg_addr(buf, lane, c);
+              const uint4 rv = lds128(a);
+              const float4 g = gamma ? __ldg(g4 + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+              sts128(a, __float_as_uint(__uint_as_float(rv.x) + g.x * x[4 * c]),
+                     __float_as_uint(__uint_as_float(rv.y) + g.y * x[4 * c + 1]),
+                     __float_as_uint(__uint_as_float(rv.z) + g.z * x[4 * c + 2]),
+                     __float_as_uint(__uint_as_float(rv.w) + g.w * x[4 * c + 3]));
+            }
+          } else if constexpr (EPI == EPI_GELU_BWD) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t a = stg_addr(buf, lane, 4 * s + c);
+              const uint4 hv = lds128(a);
+              const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+              uint32_t d[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t)
+                d[t] = pack_bf16(x[8 * c + 2 * t] * gelu_erf_grad(bf16_lo(hw[t])),
+                                 x[8 * c + 2 * t + 1] * gelu_erf_grad(bf16_hi(hw[t])));
+              sts128(a, d[0], d[1], d[2], d[3]);
+            }
+          } else if constexpr (EPI == EPI_DELTA) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t a = stg_addr(buf, lane, 4 * s + c);
+              const uint4 ov = lds128(a);
+              const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w};
+              uint32_t d[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                d[t] = pack_bf16(x[8 * c + 2 * t], x[8 * c + 2 * t + 1]);
+                dot = fmaf(bf16_lo(d[t]), bf16_lo(ow[t]), dot);   // the rounded dO the attention backward will read
+                dot = fmaf(bf16_hi(d[t]), bf16_hi(ow[t]), dot);
+              }
+              sts128(a, d[0], d[1], d[2], d[3]);
+            }
+          }
+          if (s == SUBS - 1 || idx + 1 == nvalid) {
+            if constexpr (EPI == EPI_DELTA) {
+              if (row0 + lane < M) rowstat[size_t(row0 + lane) * (N >> 6) + (col0 >> 6)] = dot;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (EPI == EPI_BIAS_GELU) {
+                const uint8_t* sb = staging + ew * 2 * kStgBuf + b * kStgBuf;
+                tma_store_2d(&tma_out, reinterpret_cast<const void*>(sb), col0, row0);
+                tma_store_2d(&tma_out2, reinterpret_cast<const void*>(sb + kStgBuf / 2), col0, row0);
+              } else {
+                tma_store_2d(&tma_out, reinterpret_cast<const void*>(staging + ew * 2 * kStgBuf + b * kStgBuf), col0, row0);
+              }
+              tma_store_commit();
+            }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&tempty[as], 0);  // release the accumulator stage to the leader's MMA thread
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
