@@ -44,6 +44,14 @@ int apla_gemm_dgrad_gelu_bwd(const void* dY, int ldy, const void* Wt, int ldwt, 
                              int M, int K_in, int N_out, apla_stream_t stream) {
   return gemm_tn(EPI_GELU_BWD, dY, Wt, M, K_in, N_out, ldy, ldwt, dH, nullptr, nullptr, nullptr, h, ldh, S(stream), 0);
 }
+int apla_gemm_bias_gelu_dgelu_fwd(const void* A, int lda, const void* W, int ldw, const float* bias, void* dgelu, void* g,
+                                  int ldo, int M, int N, int K, apla_stream_t stream) {
+  return gemm_tn(EPI_BIAS_GELU_D, A, W, M, N, K, lda, ldw, dgelu, g, bias, nullptr, nullptr, ldo, S(stream), 0);
+}
+int apla_gemm_dgrad_mul(const void* dY, int ldy, const void* Wt, int ldwt, const void* mul, void* dH, int ldh, int M,
+                        int K_in, int N_out, apla_stream_t stream) {
+  return gemm_tn(EPI_MUL_F16, dY, Wt, M, K_in, N_out, ldy, ldwt, dH, nullptr, nullptr, nullptr, mul, ldh, S(stream), 0);
+}
 int apla_gemm_dgrad_delta(const void* dY, int ldy, const void* Wt, int ldwt, const void* O, void* dO, int ldo,
                           float* delta, int M, int D, int N_out, apla_stream_t stream) {
   return gemm_tn(EPI_DELTA, dY, Wt, M, D, N_out, ldy, ldwt, dO, delta, nullptr, nullptr, O, ldo, S(stream), 0);

@@ -25,7 +25,7 @@ struct BlockPtrs {
               *ln2b = nullptr, *g1 = nullptr, *g2 = nullptr;
   float* bproj = nullptr;
   // saved activations
-  void *qkv = nullptr, *ao = nullptr, *hpre = nullptr;
+  void *qkv = nullptr, *ao = nullptr, *hpre = nullptr;  // hpre: fp16 GELU derivative of the fc1 pre-activation
   float* lse = nullptr;
 };
 
@@ -119,7 +119,7 @@ static int engine_forward(Engine* e, const float* images, const int64_t* labels,
     if (int rc = attn_fwd(b.qkv, b.ao, b.lse, nullptr, B, N, T, e->H, e->scale, s)) return rc;
     if (int rc = gemm_tn(EPI_RESID, b.ao, b.wproj, T, D, D, D, D, x_mid, nullptr, b.bproj, b.g1, x_in, D, s, 0)) return rc;
     if (int rc = layernorm_fwd(x_mid, D, b.ln2w, b.ln2b, ln_out, D, T, D, e->eps, s)) return rc;
-    if (int rc = gemm_tn(EPI_BIAS_GELU, ln_out, b.wfc1, T, Hd, D, D, D, b.hpre, gelu_out, b.bfc1, nullptr, nullptr, Hd, s, 0))
+    if (int rc = gemm_tn(EPI_BIAS_GELU_D, ln_out, b.wfc1, T, Hd, D, D, D, b.hpre, gelu_out, b.bfc1, nullptr, nullptr, Hd, s, 0))
       return rc;
     if (int rc = gemm_tn(EPI_RESID, gelu_out, b.wfc2, T, D, Hd, Hd, Hd, x_out, nullptr, b.bfc2, b.g2, x_mid, D, s, 0))
       return rc;
@@ -177,8 +177,8 @@ static int engine_backward(Engine* e, int l_from, int l_to, cudaStream_t s) {
     const BlockPtrs& b = e->blk[l];
     const float* x_in = xs + size_t(2 * l) * TD;
     const float* x_mid = xs + size_t(2 * l + 1) * TD;
-    // MLP branch: dxb holds bf16(gamma2 * dx_out)
-    if (int rc = gemm_tn(EPI_GELU_BWD, dxb, b.wfc2T, T, Hd, D, D, D, dH, nullptr, nullptr, nullptr, b.hpre, Hd, s, 0))
+    // MLP branch: dxb holds bf16(gamma2 * dx_out); hpre holds gelu'(fc1 pre-activation) in fp16
+    if (int rc = gemm_tn(EPI_MUL_F16, dxb, b.wfc2T, T, Hd, D, D, D, dH, nullptr, nullptr, nullptr, b.hpre, Hd, s, 0))
       return rc;
     if (int rc = gemm_tn(EPI_BIAS, dH, b.wfc1T, T, D, Hd, Hd, Hd, dln, nullptr, nullptr, nullptr, nullptr, D, s, 0))
       return rc;

@@ -362,8 +362,11 @@ int gemm_tn(int epi, const void* A, const void* B, int M, int N, int K, int lda,
   APLA_CHECK(epi != EPI_BIAS_GELU || out2 != nullptr, "gemm_tn: EPI_BIAS_GELU needs out2");
   APLA_CHECK((epi != EPI_RESID && epi != EPI_GELU_BWD && epi != EPI_DELTA) || aux != nullptr,
              "gemm_tn: this epilogue needs aux");
-  if (epi == EPI_DELTA) {
-    APLA_CHECK(out2 != nullptr && N % 64 == 0, "gemm_tn: EPI_DELTA needs the delta buffer in out2 and N %% 64 == 0");
+  APLA_CHECK(epi != EPI_MUL_F16 || aux != nullptr, "gemm_tn: EPI_MUL_F16 needs the fp16 multiplier in aux");
+  APLA_CHECK(epi != EPI_BIAS_GELU_D || out2 != nullptr, "gemm_tn: EPI_BIAS_GELU_D needs out2");
+  if (epi == EPI_DELTA || epi == EPI_BIAS_GELU_D || epi == EPI_MUL_F16) {   // 2-CTA kernel only
+    APLA_CHECK(epi != EPI_DELTA || (out2 != nullptr && N % 64 == 0),
+               "gemm_tn: EPI_DELTA needs the delta buffer in out2 and N %% 64 == 0");
     int bn = bn_override;
     if (bn <= 0) { const char* e = getenv("APLA_GEMM_BN"); bn = e ? atoi(e) : 0; }
     return gemm2_tn(epi, A, B, M, N, K, lda, ldb, out, out2, bias, gamma, aux, ldo, stream, bn);

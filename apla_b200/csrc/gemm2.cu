@@ -12,6 +12,8 @@
 //               memory only ever sees full 128-byte rows (the first version of this kernel wrote registers straight
 //               to global memory, 32 rows per instruction, and was LSU-wavefront-bound in every fused epilogue).
 // Epilogues: see kernels.cuh / gemm.cu header (EPI_BIAS, EPI_BIAS_GELU, EPI_RESID, EPI_GELU_BWD), plus
+//   EPI_BIAS_GELU_D  h = acc + bias[n] (fp32, not stored);  out_f16 = gelu_erf'(h);  out2_bf16 = gelu_erf(h)
+//   EPI_MUL_F16      out_bf16 = acc * aux_f16[m,n]   (fc2 dgrad times the saved GELU derivative)
 //   EPI_DELTA  out_bf16 = acc;  rowstat[m, n/64] = sum over the 64-wide head of bf16(acc) * aux_bf16[m, n]
 //              (attention-projection dgrad fused with FlashAttention's delta = rowsum(dO * O); one staging chunk is
 //              exactly one head and one thread owns one row of it, so the reduction needs no shuffles).
@@ -90,8 +92,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     tma_prefetch_desc(&tma_out);
-    if constexpr (EPI == EPI_BIAS_GELU) tma_prefetch_desc(&tma_out2);
-    if constexpr (EPI == EPI_RESID || EPI == EPI_GELU_BWD || EPI == EPI_DELTA) tma_prefetch_desc(&tma_aux);
+    if constexpr (EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_GELU_D) tma_prefetch_desc(&tma_out2);
+    if constexpr (EPI == EPI_RESID || EPI == EPI_GELU_BWD || EPI == EPI_DELTA || EPI == EPI_MUL_F16) tma_prefetch_desc(&tma_aux);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -166,11 +168,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
   } else {
     // ===================== epilogue warps (both CTAs) =====================
     constexpr bool kF32 = (EPI == EPI_RESID);
-    constexpr bool kAux = (EPI == EPI_RESID || EPI == EPI_GELU_BWD || EPI == EPI_DELTA);
-    constexpr bool kBias = (EPI != EPI_GELU_BWD && EPI != EPI_DELTA);
+    constexpr bool kAux = (EPI == EPI_RESID || EPI == EPI_GELU_BWD || EPI == EPI_DELTA || EPI == EPI_MUL_F16);
+    constexpr bool kBias = (EPI != EPI_GELU_BWD && EPI != EPI_DELTA && EPI != EPI_MUL_F16);
+    constexpr bool kTwoOut = (EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_GELU_D);
     // columns per chunk: one 128-byte staging row, except the two-output GELU epilogue which packs a 64-byte row of
     // each output (h | g) into one 4 KB buffer (64B swizzle) so that chunks can still ping-pong between buffers
-    constexpr int CW = (kF32 || EPI == EPI_BIAS_GELU) ? 32 : 64;
+    constexpr int CW = (kF32 || kTwoOut) ? 32 : 64;
     constexpr int NCH = BN / CW / 2;         // chunks per warp per tile
     constexpr int SUBS = CW / 32;            // 32-column TMEM loads per chunk
     constexpr int NSUB = NCH * SUBS;
@@ -299,6 +302,38 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
               sts128(buf + off, h[0], h[1], h[2], h[3]);
               sts128(buf + kStgBuf / 2 + off, g[0], g[1], g[2], g[3]);
             }
+          } else if constexpr (EPI == EPI_BIAS_GELU_D) {
+            // saves gelu'(h) in fp16 (|gelu'| <= 1.13: 11 mantissa bits, better than gelu' of a bf16-rounded h) so that the
+            // fc2 input-gradient epilogue is one multiply; this epilogue is store-bound, the extra math is hidden
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t dd[4], g[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                float g0, g1, d0, d1;
+                gelu_erf_both(x[8 * c + 2 * t], g0, d0);
+                gelu_erf_both(x[8 * c + 2 * t + 1], g1, d1);
+                g[t] = pack_bf16(g0, g1);
+                dd[t] = pack_f16(d0, d1);
+              }
+              const uint32_t off = lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4);   // 64B-swizzled row of 32 x 2 bytes
+              sts128(buf + off, dd[0], dd[1], dd[2], dd[3]);
+              sts128(buf + kStgBuf / 2 + off, g[0], g[1], g[2], g[3]);
+            }
+          } else if constexpr (EPI == EPI_MUL_F16) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t a = stg_addr(buf, lane, 4 * s + c);
+              const uint4 hv = lds128(a);
+              const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+              uint32_t d[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 m = unpack_f16(hw[t]);
+                d[t] = pack_bf16(x[8 * c + 2 * t] * m.x, x[8 * c + 2 * t + 1] * m.y);
+              }
+              sts128(a, d[0], d[1], d[2], d[3]);
+            }
           } else if constexpr (EPI == EPI_RESID) {
             const float4* g4 = reinterpret_cast<const float4*>(gamma ? gamma + col : nullptr);
 #pragma unroll
@@ -347,7 +382,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              if constexpr (EPI == EPI_BIAS_GELU) {
+              if constexpr (kTwoOut) {
                 const uint8_t* sb = staging + ew * 2 * kStgBuf + b * kStgBuf;
                 tma_store_2d(&tma_out, reinterpret_cast<const void*>(sb), col0, row0);
                 tma_store_2d(&tma_out2, reinterpret_cast<const void*>(sb + kStgBuf / 2), col0, row0);
@@ -382,7 +417,7 @@ static int launch(const void* A, const void* B, int M, int N, int K, int lda, in
   if (int rc = make_tmap_2d(&ta, A, 2, M, K, lda, BM, BK, true)) return rc;
   if (int rc = make_tmap_2d(&tb, B, 2, N, K, ldb, BN / 2, BK, true)) return rc;
   constexpr int oelt = (EPI == EPI_RESID) ? 4 : 2;
-  if (EPI == EPI_BIAS_GELU) {
+  if (EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_GELU_D) {
     if (int rc = make_tmap_2d_sw(&to, out, 2, M, N, ldo, 32, 32, 64)) return rc;
     if (int rc = make_tmap_2d_sw(&to2, out2, 2, M, N, ldo, 32, 32, 64)) return rc;
   } else {
@@ -390,7 +425,7 @@ static int launch(const void* A, const void* B, int M, int N, int K, int lda, in
     to2 = to;
   }
   tx = to;
-  if (EPI == EPI_RESID || EPI == EPI_GELU_BWD || EPI == EPI_DELTA)
+  if (EPI == EPI_RESID || EPI == EPI_GELU_BWD || EPI == EPI_DELTA || EPI == EPI_MUL_F16)
     if (int rc = make_tmap_2d(&tx, aux, oelt, M, N, ldo, 32, 128 / oelt, true)) return rc;
   auto kern = gemm2_kernel<BN, EPI>;
   static bool attr_set = false;
@@ -436,6 +471,10 @@ int gemm2_tn(int epi, const void* A, const void* B, int M, int N, int K, int lda
       return g2::dispatch<EPI_GELU_BWD>(A, B, M, N, K, lda, ldb, out, out2, bias, gamma, aux, ldo, stream, bn);
     case EPI_DELTA:
       return g2::dispatch<EPI_DELTA>(A, B, M, N, K, lda, ldb, out, out2, bias, gamma, aux, ldo, stream, bn);
+    case EPI_BIAS_GELU_D:
+      return g2::dispatch<EPI_BIAS_GELU_D>(A, B, M, N, K, lda, ldb, out, out2, bias, gamma, aux, ldo, stream, bn);
+    case EPI_MUL_F16:
+      return g2::dispatch<EPI_MUL_F16>(A, B, M, N, K, lda, ldb, out, out2, bias, gamma, aux, ldo, stream, bn);
   }
   set_error("gemm2_tn: unknown epilogue %d", epi);
   return 1;

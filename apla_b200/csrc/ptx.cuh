@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -314,5 +315,23 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float t = 1.0f - s;
   return fmaf(x * d * s, t, s);                 // Phi + x * Phi (1 - Phi) u'
 }
+
+// gelu(x) and gelu'(x) from one exponential (the fc1 epilogue that saves the derivative instead of the pre-activation)
+__device__ __forceinline__ void gelu_erf_both(float x, float& g, float& d) {
+  const float x2 = fminf(x * x, 49.0f);
+  float p = fmaf(x2, kGeluC2 * kNegLog2e, kGeluC1 * kNegLog2e);
+  p = fmaf(x2, p, kGeluC0 * kNegLog2e);
+  float u1 = fmaf(x2, 5.0f * kGeluC2, 3.0f * kGeluC1);
+  u1 = fmaf(x2, u1, kGeluC0);
+  const float e = ex2_approx(x * p);
+  const float s = rcp_approx(1.0f + e);
+  g = x * s;
+  d = fmaf(x * u1 * s, 1.0f - s, s);
+}
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_f16(uint32_t v) { return __half22float2(*reinterpret_cast<__half2*>(&v)); }
 
 }  // namespace apla

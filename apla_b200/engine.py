@@ -11,7 +11,7 @@ gradient all-reduce.  All step arithmetic is in libapla_b200.so; nothing falls b
 
 Memory layout in HBM (T = B*N tokens, D embed, L blocks), sized for B=64 ViT-B/14 (~5 GB of 180 GB):
   xs        fp32 [2L+1, T, D]   residual-stream checkpoints (block input / after attention / ... / final)
-  qkv[l]    bf16 [T, 3D]  ao[l] bf16 [T, D]  lse[l] fp32 [T, H]  hpre[l] bf16 [T, 4D]     saved for backward
+  qkv[l]    bf16 [T, 3D]  ao[l] bf16 [T, D]  lse[l] fp32 [T, H]  hpre[l] fp16 [T, 4D] (gelu' of the fc1 pre-activation)   saved for backward
   ln_out, gelu_out, dx, dxb, dO, dqkv, dsub, delta                                         transients, reused
   params / grads / exp_avg / exp_avg_sq   fp32 arenas [W1 x L | fc.weight | b1 x L | fc.bias]  (one all-reduce)
 """
@@ -184,7 +184,7 @@ class FineTuneEngine:
             self._set("g2", self._dev(g2, F32) if g2 is not None else None, l)
             self._set("qkv", self._new(T, 3 * D), l)
             self._set("ao", self._new(T, D), l)
-            self._set("hpre", self._new(T, hidden), l)
+            self._set("hpre", self._new(T, hidden, dtype=torch.float16), l)
             self._set("lse", self._new(T, H, dtype=F32), l)
 
         # ---- head ----

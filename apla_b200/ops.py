@@ -76,6 +76,35 @@ def gemm_dgrad(dy, wt, out=None):
     return out
 
 
+def gemm_bias_gelu_dgelu(a, w, bias=None, d=None, g=None):
+    """g_bf16 = gelu(a @ w^T + bias), d_f16 = gelu'(a @ w^T + bias): fc1 forward that saves the derivative."""
+    require_device()
+    _chk(a, BF16, "a", 2); _chk(w, BF16, "w", 2)
+    M, K = a.shape; N = w.shape[0]
+    if d is None:
+        d = torch.empty(M, N, device=a.device, dtype=torch.float16)
+    if g is None:
+        g = torch.empty(M, N, device=a.device, dtype=BF16)
+    _chk(d, torch.float16, "d", 2); _chk(g, BF16, "g", 2)
+    assert _ld(d) == _ld(g)
+    LIB.call("apla_gemm_bias_gelu_dgelu_fwd", ptr(a), _ld(a), ptr(w), _ld(w), ptr(bias), ptr(d), ptr(g), _ld(d), M, N, K,
+             stream())
+    return d, g
+
+
+def gemm_dgrad_mul(dy, wt, mul, out=None):
+    """dH_bf16 = (dy @ wt^T) * mul_f16."""
+    require_device()
+    _chk(dy, BF16, "dy", 2); _chk(wt, BF16, "wt", 2); _chk(mul, torch.float16, "mul", 2)
+    M, Nout = dy.shape; Kin = wt.shape[0]
+    if out is None:
+        out = torch.empty(M, Kin, device=dy.device, dtype=BF16)
+    assert _ld(out) == _ld(mul)
+    LIB.call("apla_gemm_dgrad_mul", ptr(dy), _ld(dy), ptr(wt), _ld(wt), ptr(mul), ptr(out), _ld(out), M, Kin, Nout,
+             stream())
+    return out
+
+
 def gemm_dgrad_delta(dy, wt, o, out=None, delta=None):
     """dO[M,D] = dy @ wt^T and delta[M, D/64] = per-head rowsum(dO * o): projection dgrad + attention-backward delta."""
     require_device()

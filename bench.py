@@ -156,20 +156,20 @@ def time_dominant_kernel(eng, torch, iters=24):
     T, D, Hd, L = sh["T"], sh["D"], sh["hidden"], sh["L"]
     x = torch.randn(T, D, device="cuda").to(torch.bfloat16)
     ws = [(torch.randn(Hd, D, device="cuda") * 0.02).to(torch.bfloat16) for _ in range(4)]
-    hs = [torch.empty(T, Hd, device="cuda", dtype=torch.bfloat16) for _ in range(4)]
+    hs = [torch.empty(T, Hd, device="cuda", dtype=torch.float16) for _ in range(4)]
     gs = [torch.empty(T, Hd, device="cuda", dtype=torch.bfloat16) for _ in range(4)]
     bias = torch.zeros(Hd, device="cuda")
     for i in range(4):
-        ops.gemm_bias_gelu(x, ws[i], bias, h=hs[i], g=gs[i])
+        ops.gemm_bias_gelu_dgelu(x, ws[i], bias, d=hs[i], g=gs[i])
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for i in range(iters):
-        ops.gemm_bias_gelu(x, ws[i % 4], bias, h=hs[i % 4], g=gs[i % 4])
+        ops.gemm_bias_gelu_dgelu(x, ws[i % 4], bias, d=hs[i % 4], g=gs[i % 4])
     b.record()
     torch.cuda.synchronize()
     sec = a.elapsed_time(b) * 1e-3 / iters
-    return dict(kernel="gemm_kernel<256,EPI_BIAS_GELU> (Mlp.fc1+GELU, 16448x3072x768)", us=sec * 1e6,
+    return dict(kernel="gemm2_kernel<256,EPI_BIAS_GELU_D> (Mlp.fc1 + GELU + saved GELU', 16448x3072x768)", us=sec * 1e6,
                 tflops=2.0 * T * D * Hd / sec / 1e12)
 
 

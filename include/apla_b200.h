@@ -52,6 +52,14 @@ int apla_gemm_dgrad(const void* dY, int ldy, const void* Wt, int ldwt, void* dX,
 /* dH_bf16 = (dY . Wt^T) * gelu_erf'(h_bf16): fc2 input gradient fused with GELU backward (vit.py:164-166). */
 int apla_gemm_dgrad_gelu_bwd(const void* dY, int ldy, const void* Wt, int ldwt, const void* h, void* dH, int ldh,
                              int M, int K_in, int N_out, apla_stream_t stream);
+/* Training variant of the pair above (what the step engine runs): the forward saves the GELU derivative instead of
+ * the pre-activation -- dgelu_f16 = gelu_erf'(A . W^T + bias), g_bf16 = gelu_erf(A . W^T + bias), both from the fp32
+ * accumulator -- and the fc2 input gradient becomes dH_bf16 = (dY . Wt^T) * mul_f16.  Same autograd result as
+ * nn.GELU backward (vit.py:164), one multiply in the epilogue instead of an erf evaluation. */
+int apla_gemm_bias_gelu_dgelu_fwd(const void* A, int lda, const void* W, int ldw, const float* bias, void* dgelu,
+                                  void* g, int ldo, int M, int N, int K, apla_stream_t stream);
+int apla_gemm_dgrad_mul(const void* dY, int ldy, const void* Wt, int ldwt, const void* mul, void* dH, int ldh, int M,
+                        int K_in, int N_out, apla_stream_t stream);
 /* dO_bf16[M,D] = dY_bf16[M,D_out] . Wt^T  and  delta_f32[M, D/64] = rowsum over each 64-wide head of dO * O_bf16:
  * the input gradient of the attention projection (backward of appla_attn.py:64-79) fused with the softmax-backward
  * row term of the attention that produced O (appla_attn.py:58-62); pass the result to apla_attn_bwd with out = NULL. */

@@ -103,6 +103,26 @@ def test_gemm_dgrad_and_gelu_bwd():
     assert rel(dh.float(), hh.grad) < 5e-3
 
 
+def test_gemm_gelu_saved_derivative():
+    """fc1 forward saving gelu'(h) in fp16 + fc2 dgrad multiplying by it == autograd through nn.GELU (fp32 reference)."""
+    ops = _cuda()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    M, Din, Dh = 900, 384, 1536
+    a = bf(torch.randn(M, Din, device="cuda", generator=g))
+    w1 = bf(torch.randn(Dh, Din, device="cuda", generator=g) * 0.08)
+    b1 = torch.randn(Dh, device="cuda", generator=g) * 0.3
+    d, gl = ops.gemm_bias_gelu_dgelu(a, w1, b1)
+    h = (a.float() @ w1.float().t() + b1).requires_grad_(True)
+    gref = torch.nn.functional.gelu(h)
+    assert rel(gl.float(), gref.detach()) < 4e-3
+    dy = bf(torch.randn(M, Din, device="cuda", generator=g))
+    W2 = bf(torch.randn(Din, Dh, device="cuda", generator=g) * 0.05)      # fc2 weight [out, in]
+    dh = ops.gemm_dgrad_mul(dy, W2.t().contiguous(), d)
+    gref.backward(dy.float() @ W2.float())
+    assert rel(d.float(), torch.autograd.grad(torch.nn.functional.gelu(h).sum(), h)[0]) < 1e-3
+    assert rel(dh.float(), h.grad) < 4e-3
+
+
 @pytest.mark.parametrize("M,D", [(514, 768), (1576, 384), (16448, 768)])
 def test_gemm_dgrad_delta(M, D):
     """Projection dgrad with the fused delta = rowsum(dO * O) per (token, head) epilogue."""

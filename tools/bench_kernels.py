@@ -50,6 +50,9 @@ def main():
     h = torch.empty(T, 4 * D, device=dev, dtype=torch.bfloat16); g = torch.empty_like(h)
     t = timeit(lambda: ops.gemm_bias_gelu(x, w, torch.zeros(4 * D, device=dev), h=h, g=g))
     res.append(("gemm_bias_gelu fc1", t, 2 * T * 4 * D * D / t / 1e12, "TFLOP/s"))
+    dsave = torch.empty(T, 4 * D, device=dev, dtype=torch.float16)
+    t = timeit(lambda: ops.gemm_bias_gelu_dgelu(x, w, torch.zeros(4 * D, device=dev), d=dsave, g=g))
+    res.append(("gemm_bias_gelu_dgelu fc1", t, 2 * T * 4 * D * D / t / 1e12, "TFLOP/s"))
     w2 = (torch.randn(D, 4 * D, device=dev) * 0.02).bfloat16()
     resid = torch.randn(T, D, device=dev)
     t = timeit(lambda: ops.gemm_bias_ls_residual(x4, w2, None, None, resid, out=resid))
@@ -61,6 +64,8 @@ def main():
     dh = torch.empty(T, 4 * D, device=dev, dtype=torch.bfloat16)
     t = timeit(lambda: ops.gemm_dgrad_gelu_bwd(x, w2t, h, out=dh))
     res.append(("gemm_dgrad_gelu_bwd fc2", t, 2 * T * 4 * D * D / t / 1e12, "TFLOP/s"))
+    t = timeit(lambda: ops.gemm_dgrad_mul(x, w2t, dsave, out=dh))
+    res.append(("gemm_dgrad_mul fc2", t, 2 * T * 4 * D * D / t / 1e12, "TFLOP/s"))
     # LN
     xf = torch.randn(T, D, device=dev); wln = torch.ones(D, device=dev); bln = torch.zeros(D, device=dev)
     y = torch.empty(T, D, device=dev, dtype=torch.bfloat16)
