@@ -162,44 +162,50 @@ struct Walk {
   __device__ __forceinline__ int valid_cols(int j) const { return min(CW, n - j * CW); }
 };
 
-// One chunk of one row, two passes over the CW score columns in TMEM (row maximum, then P = exp2(S*sl2 - ms) packed to
-// bf16 and written over S in place).  Each pass keeps two 32-column pieces in registers: the load of the third piece
-// is in flight while the second is processed (tcgen05.wait::ld waits for every outstanding load, so the pieces are
-// paired rather than individually awaited).  FULL: all CW columns are valid keys (no masking).
+// One chunk of one row.  The compute warpgroups run with 184 registers (setmaxnreg; the producer / issuer / helper
+// warpgroups give theirs up), so all CW = 96 scores of the row are loaded from TMEM ONCE, by three back-to-back
+// tcgen05.ld behind a single wait, and stay in registers for the row maximum and for P = exp2(S*sl2 - ms), which is
+// packed to bf16 and written over S in place.  (The first version made two passes over TMEM with two 32-column
+// pieces in flight; its four exposed TMEM round trips per chunk were more than half of the softmax time.)
+// FULL: all CW columns are valid keys (no masking).
 template <bool FULL>
-__device__ __forceinline__ float piece_max(const uint32_t (&v)[32], int valid, int base, float m) {
-#pragma unroll
-  for (int i = 0; i < 32; i += 2) {
-    if (FULL) {
-      m = fmaxf(m, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-    } else {
-      if (base + i < valid) m = fmaxf(m, __uint_as_float(v[i]));
-      if (base + i + 1 < valid) m = fmaxf(m, __uint_as_float(v[i + 1]));
-    }
-  }
-  return m;
-}
-template <bool FULL>
-__device__ __forceinline__ float chunk_row_max(uint32_t t_s, int valid, int n_mma) {
-  uint32_t a[32], b[32];
-  float m = -INFINITY;
+__device__ __forceinline__ void chunk_load(uint32_t t_s, int n_mma, uint32_t (&a)[32], uint32_t (&b)[32],
+                                           uint32_t (&c)[32]) {
   tmem_ld_32x32(t_s, a);
   if (FULL || n_mma > 32) tmem_ld_32x32(t_s + 32, b);
+  if (FULL || n_mma > 64) tmem_ld_32x32(t_s + 64, c);
   tmem_ld_wait();
-  // (a piece whose 32 columns are all valid takes the unmasked code even in a partial chunk)
-  m = (FULL || valid >= 32) ? piece_max<true>(a, valid, 0, m) : piece_max<false>(a, valid, 0, m);
-  if (FULL || n_mma > 64) tmem_ld_32x32(t_s + 64, a);
-  if (FULL || n_mma > 32) m = (FULL || valid >= 64) ? piece_max<true>(b, valid, 32, m) : piece_max<false>(b, valid, 32, m);
-  if (FULL || n_mma > 64) {
-    tmem_ld_wait();
-    m = FULL ? piece_max<true>(a, valid, 64, m) : piece_max<false>(a, valid, 64, m);
+}
+template <bool FULL>
+__device__ __forceinline__ float piece_max(const uint32_t (&v)[32], int valid, int base) {
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    if (FULL) {
+      m0 = fmaxf(m0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+      m1 = fmaxf(m1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+    } else {
+      if (base + i < valid) m0 = fmaxf(m0, __uint_as_float(v[i]));
+      if (base + i + 1 < valid) m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+      if (base + i + 2 < valid) m0 = fmaxf(m0, __uint_as_float(v[i + 2]));
+      if (base + i + 3 < valid) m1 = fmaxf(m1, __uint_as_float(v[i + 3]));
+    }
   }
+  return fmaxf(m0, m1);
+}
+template <bool FULL>
+__device__ __forceinline__ float chunk_row_max(const uint32_t (&a)[32], const uint32_t (&b)[32], const uint32_t (&c)[32],
+                                               int valid, int n_mma) {
+  // (a piece whose 32 columns are all valid takes the unmasked code even in a partial chunk)
+  float m = (FULL || valid >= 32) ? piece_max<true>(a, valid, 0) : piece_max<false>(a, valid, 0);
+  if (FULL || n_mma > 32) m = fmaxf(m, (FULL || valid >= 64) ? piece_max<true>(b, valid, 32) : piece_max<false>(b, valid, 32));
+  if (FULL || n_mma > 64) m = fmaxf(m, FULL ? piece_max<true>(c, valid, 64) : piece_max<false>(c, valid, 64));
   return m;
 }
 template <bool FULL>
-__device__ __forceinline__ void piece_exp(uint32_t t_p, const uint32_t (&v)[32], int valid, int base, float sl2, float ms,
-                                          float& rs0, float& rs1) {
+__device__ __forceinline__ float piece_exp(uint32_t t_p, const uint32_t (&v)[32], int valid, int base, float sl2, float ms) {
   uint32_t pk[16];
+  float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, -ms));
@@ -213,28 +219,17 @@ __device__ __forceinline__ void piece_exp(uint32_t t_p, const uint32_t (&v)[32],
     pk[i] = pack_bf16(p0, p1);
   }
   tmem_st_32x16(t_p, pk);
-}
-// (piece pc of P lands in columns [16 pc, 16 pc + 16), which belong to score pieces that are already in registers)
-template <bool FULL>
-__device__ __forceinline__ float chunk_exp(uint32_t t_s, int valid, int n_mma, float sl2, float ms) {
-  uint32_t a[32], b[32];
-  float rs0 = 0.f, rs1 = 0.f;
-  tmem_ld_32x32(t_s, a);
-  if (FULL || n_mma > 32) tmem_ld_32x32(t_s + 32, b);
-  tmem_ld_wait();
-  if (FULL || valid >= 32) piece_exp<true>(t_s, a, valid, 0, sl2, ms, rs0, rs1);
-  else piece_exp<false>(t_s, a, valid, 0, sl2, ms, rs0, rs1);
-  if (FULL || n_mma > 64) tmem_ld_32x32(t_s + 64, a);
-  if (FULL || n_mma > 32) {
-    if (FULL || valid >= 64) piece_exp<true>(t_s + 16, b, valid, 32, sl2, ms, rs0, rs1);
-    else piece_exp<false>(t_s + 16, b, valid, 32, sl2, ms, rs0, rs1);
-  }
-  if (FULL || n_mma > 64) {
-    tmem_ld_wait();
-    if (FULL) piece_exp<true>(t_s + 32, a, valid, 64, sl2, ms, rs0, rs1);
-    else piece_exp<false>(t_s + 32, a, valid, 64, sl2, ms, rs0, rs1);
-  }
   return rs0 + rs1;
+}
+// (piece pc of P lands in columns [16 pc, 16 pc + 16) of the slot; every score is already in registers)
+template <bool FULL>
+__device__ __forceinline__ float chunk_exp(uint32_t t_s, const uint32_t (&a)[32], const uint32_t (&b)[32],
+                                           const uint32_t (&c)[32], int valid, int n_mma, float sl2, float ms) {
+  float rs = (FULL || valid >= 32) ? piece_exp<true>(t_s, a, valid, 0, sl2, ms) : piece_exp<false>(t_s, a, valid, 0, sl2, ms);
+  if (FULL || n_mma > 32)
+    rs += (FULL || valid >= 64) ? piece_exp<true>(t_s + 16, b, valid, 32, sl2, ms) : piece_exp<false>(t_s + 16, b, valid, 32, sl2, ms);
+  if (FULL || n_mma > 64) rs += FULL ? piece_exp<true>(t_s + 32, c, valid, 64, sl2, ms) : piece_exp<false>(t_s + 32, c, valid, 64, sl2, ms);
+  return rs;
 }
 
 struct Maps {
@@ -298,8 +293,11 @@ attn_fwd_sr_kernel(const __grid_constant__ Maps maps, const __nv_bfloat16* __res
   const long long tr_t0 = tr_t0_s;
 #endif
 
+  // Register budget per warpgroup (65536 = 128 x 64 + 256 x 184 + 128 x 80; setmaxnreg at the head of every role
+  // branch): the softmax keeps a whole 96-score row live.
   if (warp == 0) {
     // ------------------------------------------------------------------------------------------------ producer
+    reg_dealloc<64>();
     // (the whole warp walks the schedule -- Walk uses warp shuffles -- and lane 0 issues the copies)
     Walk k;
     k.init(prob);
@@ -339,6 +337,7 @@ attn_fwd_sr_kernel(const __grid_constant__ Maps maps, const __nv_bfloat16* __res
     // One issuer warp per stream (items of even / odd index); chunk k of the stream's chunk sequence lives in S slot
     // k & 1.  Order: S(0), S(1), then for every k: [P(k) ready] PV(k), S(k+2).  A score MMA whose operands have not
     // landed yet is not waited for (the rows may be held up by a buffer that only this stream's next PV releases).
+    reg_dealloc<64>();
     const int w = warp - 1;
     const bool leader = elect_one();
     PROF_DECL;
@@ -442,8 +441,11 @@ attn_fwd_sr_kernel(const __grid_constant__ Maps maps, const __nv_bfloat16* __res
       else if (++spins > (1u << 24)) __trap();
     }
     PROF_DUMP("issuer(p_full)");
+  } else if (warp == 3) {
+    reg_dealloc<64>();   // idle warp of the first warpgroup: every warp of a warpgroup executes the same setmaxnreg
   } else if (warp >= 12) {
     // ------------------------------------------------------------------------------------------------ helpers
+    reg_dealloc<80>();
     // Query rows 256.. of a 257/258-token sequence on CUDA cores (4 warps, fp32): scores against the resident K,
     // softmax, P.V against the resident V.  The helpers also take part in releasing every group's K/V buffer.
     const int e = threadIdx.x - 384, hw = warp - 12;
@@ -530,6 +532,7 @@ attn_fwd_sr_kernel(const __grid_constant__ Maps maps, const __nv_bfloat16* __res
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------------------------------------ compute
+    reg_alloc<184>();
     const int w = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;                  // row of the q tile == TMEM lane
@@ -566,7 +569,10 @@ attn_fwd_sr_kernel(const __grid_constant__ Maps maps, const __nv_bfloat16* __res
         if (tile_active) {
           // pass 1: row maximum of the chunk
           const bool full = valid == CW;
-          const float mx = full ? chunk_row_max<true>(t_s, valid, n_mma) : chunk_row_max<false>(t_s, valid, n_mma);
+          uint32_t va[32], vb[32], vc[32];
+          if (full) chunk_load<true>(t_s, n_mma, va, vb, vc);
+          else chunk_load<false>(t_s, n_mma, va, vb, vc);
+          const float mx = full ? chunk_row_max<true>(va, vb, vc, valid, n_mma) : chunk_row_max<false>(va, vb, vc, valid, n_mma);
           if (j == 0) {
             m_used = mx;
           } else {
@@ -591,7 +597,8 @@ attn_fwd_sr_kernel(const __grid_constant__ Maps maps, const __nv_bfloat16* __res
           }
           // pass 2: the exponentials
           const float ms = m_used * sl2;
-          const float rs = full ? chunk_exp<true>(t_s, valid, n_mma, sl2, ms) : chunk_exp<false>(t_s, valid, n_mma, sl2, ms);
+          const float rs = full ? chunk_exp<true>(t_s, va, vb, vc, valid, n_mma, sl2, ms)
+                                : chunk_exp<false>(t_s, va, vb, vc, valid, n_mma, sl2, ms);
           l_run += rs;
           tmem_st_wait();
         }

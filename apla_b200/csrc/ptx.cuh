@@ -251,6 +251,17 @@ __device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&v)[32]) {
                : "memory");
 }
 
+// Warpgroup register re-allocation (setmaxnreg): data-movement / issuer warpgroups hand registers to the compute
+// warpgroups.  Every warp of a warpgroup (4 consecutive warps) must execute the same instruction.
+template <int N>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // ----------------------------------------------------------------------------------------------
 // descriptors
 // ----------------------------------------------------------------------------------------------
