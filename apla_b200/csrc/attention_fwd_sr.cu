@@ -234,6 +234,7 @@ __device__ __forceinline__ float chunk_exp(uint32_t t_s, const uint32_t (&a)[32]
 
 struct Maps {
   CUtensorMap q128, kv64, kv16;   // 128-row boxes for Q tiles, 64- and 16-row boxes for the resident K / V rows
+  CUtensorMap o32;                // 32-row x 64-column boxes of the output (one warp's rows of one head)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -260,13 +261,14 @@ attn_fwd_sr_kernel(const __grid_constant__ Maps maps, const __nv_bfloat16* __res
     tma_prefetch_desc(&maps.q128);
     tma_prefetch_desc(&maps.kv64);
     tma_prefetch_desc(&maps.kv16);
+    tma_prefetch_desc(&maps.o32);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 3);   // both issuers and the helper warps
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 1);
+      mbar_init(&q_empty[i], 5);   // the issuer's last score MMA + the four warps of the item's compute warpgroup
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
@@ -614,34 +616,61 @@ attn_fwd_sr_kernel(const __grid_constant__ Maps maps, const __nv_bfloat16* __res
       }
       // epilogue: O / l -> bf16 -> global, lse
       PW(2, consume_pv(kc));
+      if (quad == 0) TR(2 + w, 0x81);
       tc_fence_after();
+      // O / l -> bf16.  A warp whose 32 rows all exist stages them (128B-swizzled) in ITS rows of the item's Q tile slot
+      // -- every MMA that read the slot has completed -- and writes them with one TMA store; per-thread 16-byte stores
+      // to 32 different rows cost ~2500 cycles per item here.  The slot goes back to the producer once the store has
+      // read it.  Warps with a partial or empty row range keep the per-row stores.
       if (tile_active) {
         const int r = k.t * 128 + row;
         const bool store = r < k.n;
+        const bool whole = k.t * 128 + quad * 32 + 32 <= k.n;   // warp-uniform
         const float inv = 1.f / l_run;
         uint4* dst = reinterpret_cast<uint4*>(out + size_t(k.row_start + (store ? r : 0)) * D + k.h * 64);
+        const uint32_t stage = smem_u32(smem + OFF_Q + (k.ii & 3) * QT_BYTES + quad * 4096);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t ov[32];
           tmem_ld_32x32(lane_addr + TM_O + c * 32, ov);
           tmem_ld_wait();
-          if (store) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float x[8];
+          for (int i = 0; i < 4; ++i) {
+            float x[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(ov[8 * i + e]) * inv;
-              dst[c * 4 + i] =
-                  make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(ov[8 * i + e]) * inv;
+            const uint4 pk =
+                make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+            if (whole) {
+              const uint32_t a = stage + lane * 128 + (((c * 4 + i) ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w)
+                           : "memory");
+            } else if (store) {
+              dst[c * 4 + i] = pk;
             }
           }
         }
+        if (quad == 0) TR(2 + w, 0x82);
         if (store) lse[size_t(k.row_start + r) * H + k.h] = m_used * scale + logf(l_run);
+        if (whole) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&maps.o32, smem + OFF_Q + (k.ii & 3) * QT_BYTES + quad * 4096, k.h * 64,
+                         k.row_start + k.t * 128 + quad * 32);
+            tma_store_commit();
+            tma_store_wait_read<0>();
+          }
+        }
       }
+      __syncwarp();
+      if (quad == 0) TR(2 + w, 0x83);
+      if (lane == 0) mbar_arrive(&q_empty[k.ii & 3]);
       tc_fence_before();
       if (quad == 0) TR(2 + w, 0x80);
       k.next_item(prob);
     }
+    if (lane == 0) tma_store_wait<0>();
     if (quad == 2) PROF_DUMP("compute(s_full, o_full in-chunk, o_full epilogue, busy, chunks)");
   }
   __syncwarp();
@@ -674,6 +703,7 @@ int attn_fwd_sr(const void* qkv, void* out, float* lse, const int* cu_seqlens, i
   if (int rc = make_tmap_2d(&m.q128, qkv, 2, T, 3 * D, 3 * D, 128, 64, true)) return rc;
   if (int rc = make_tmap_2d(&m.kv64, qkv, 2, T, 3 * D, 3 * D, 64, 64, true)) return rc;
   if (int rc = make_tmap_2d(&m.kv16, qkv, 2, T, 3 * D, 3 * D, 16, 64, true)) return rc;
+  if (int rc = make_tmap_2d(&m.o32, out, 2, T, D, D, 32, 64, true)) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     APLA_CUDA(cudaFuncSetAttribute(attn_fwd_sr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
