@@ -226,9 +226,18 @@ static int engine_optim(Engine* e, float gscale, float max_norm, float lr, float
   if (int rc = adamw_step(params, grads, e->get<float>("exp_avg"), e->get<float>("exp_avg_sq"), ar.n, ar.n_decay, sumsq,
                           gscale, max_norm, lr, wd, b1, b2, eps, step, s))
     return rc;
-  // refresh the dense bf16 projection copies from the updated fp32 rows
+  // refresh the dense bf16 projection copies from the updated fp32 rows: one launch when the host laid the per-block
+  // copies out back to back (apla_b200/engine.py does), one launch per block otherwise
   const int L = e->L, r = e->r, D = e->D;
-  // blocks' dense copies are separate allocations: refresh one block per launch row via per-block pointers
+  bool packed = true;
+  for (int l = 1; l < L; ++l) {
+    packed = packed && reinterpret_cast<char*>(e->blk[l].wproj) == reinterpret_cast<char*>(e->blk[0].wproj) + size_t(l) * D * D * 2 &&
+             reinterpret_cast<char*>(e->blk[l].wprojT) == reinterpret_cast<char*>(e->blk[0].wprojT) + size_t(l) * D * D * 2 &&
+             e->blk[l].bproj == e->blk[0].bproj + size_t(l) * D;
+  }
+  if (packed)
+    return proj_refresh(params + ar.w1, params + ar.b1, e->get<int>("idx"), e->blk[0].wproj, e->blk[0].wprojT,
+                        e->blk[0].bproj, L, r, D, int64_t(r) * D, r, s);
   for (int l = 0; l < L; ++l) {
     if (int rc = proj_refresh(params + ar.w1 + size_t(l) * r * D, params + ar.b1 + size_t(l) * r,
                               e->get<int>("idx") + size_t(l) * r, e->blk[l].wproj, e->blk[l].wprojT, e->blk[l].bproj, 1, r,

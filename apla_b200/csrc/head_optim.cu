@@ -80,22 +80,27 @@ __global__ void head_wgrad_kernel(const float* __restrict__ dlogits, const __nv_
 }
 
 // dxn[b,d] = sum_c dlogits[b,c] * W[c,d]  -> bf16 (gradient w.r.t. the final LayerNorm output)
-__global__ void head_dgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ W,
-                                  __nv_bfloat16* __restrict__ dxn, int B, int D, int C) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * D) return;
-  const int b = i / D, d = i % D;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // independent chains: the loop is latency-bound
-  int c = 0;
-  for (; c + 4 <= C; c += 4) {
-    const float* dl = dlogits + size_t(b) * C + c;
-    acc0 += __ldg(dl) * __ldg(W + size_t(c) * D + d);
-    acc1 += __ldg(dl + 1) * __ldg(W + size_t(c + 1) * D + d);
-    acc2 += __ldg(dl + 2) * __ldg(W + size_t(c + 2) * D + d);
-    acc3 += __ldg(dl + 3) * __ldg(W + size_t(c + 3) * D + d);
+// One block per (64-column slice of d, image b): 4 groups of 64 threads split the classes, 8 independent loads in
+// flight per thread (the first version ran one 555-step dependent loop per output and took 80 us).
+__global__ void __launch_bounds__(256)
+head_dgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ W, __nv_bfloat16* __restrict__ dxn, int B,
+                  int D, int C) {
+  __shared__ float red[4][64];
+  const int b = blockIdx.y, d = blockIdx.x * 64 + (threadIdx.x & 63), part = threadIdx.x >> 6;
+  const float* dl = dlogits + size_t(b) * C;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (d < D) {
+    int c = part;
+    for (; c + 28 < C; c += 32) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] = fmaf(__ldg(dl + c + 4 * u), __ldg(W + size_t(c + 4 * u) * D + d), acc[u]);
+    }
+    for (; c < C; c += 4) acc[0] = fmaf(__ldg(dl + c), __ldg(W + size_t(c) * D + d), acc[0]);
   }
-  for (; c < C; ++c) acc0 += __ldg(dlogits + size_t(b) * C + c) * __ldg(W + size_t(c) * D + d);
-  dxn[i] = __float2bfloat16_rn((acc0 + acc1) + (acc2 + acc3));
+  red[part][threadIdx.x & 63] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  __syncthreads();
+  if (part == 0 && d < D)
+    dxn[size_t(b) * D + d] = __float2bfloat16_rn((red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -189,7 +194,7 @@ int head_bwd(const float* dlogits, const void* xn, const float* W, float* dW, fl
   head_wgrad_kernel<<<cdiv(C * D, 256), 256, 0, s>>>(dlogits, reinterpret_cast<const __nv_bfloat16*>(xn), dW, db, B, D, C);
   APLA_CUDA(cudaGetLastError());
   count_launch();
-  head_dgrad_kernel<<<cdiv(B * D, 256), 256, 0, s>>>(dlogits, W, reinterpret_cast<__nv_bfloat16*>(dxn), B, D, C);
+  head_dgrad_kernel<<<dim3(cdiv(D, 64), B), 256, 0, s>>>(dlogits, W, reinterpret_cast<__nv_bfloat16*>(dxn), B, D, C);
   APLA_CUDA(cudaGetLastError());
   count_launch();
   return 0;

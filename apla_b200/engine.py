@@ -133,6 +133,10 @@ class FineTuneEngine:
 
         idx_all = torch.zeros(L, r, dtype=torch.int32)
         rowmap_all = torch.full((L, D), -1, dtype=torch.int32)
+        # dense projection copies of all blocks back to back: refreshed by ONE kernel after every optimiser step
+        self._wproj_all = self._new(L, D, D)
+        self._wprojT_all = self._new(L, D, D)
+        self._bproj_all = self._new(L, D, dtype=F32)
         # ---- blocks ----
         for l, blk in enumerate(bb.blocks):
             at = blk.attn
@@ -169,12 +173,15 @@ class FineTuneEngine:
                 b = mod.bias.detach().float() if mod.bias is not None else torch.zeros(w.shape[0])
                 return self._dev(w, BF16), self._dev(w.t(), BF16), self._dev(b, F32)
 
+            self._wproj_all[l].copy_(w_full.to(self.device))
+            self._wprojT_all[l].copy_(w_full.t().to(self.device))
+            self._bproj_all[l].copy_(b_full.to(self.device))
             wqkv, wqkvT, bqkv = lin(at.qkv)
             wfc1, wfc1T, bfc1 = lin(blk.mlp.fc1)
             wfc2, wfc2T, bfc2 = lin(blk.mlp.fc2)
             for k, v in dict(wqkv=wqkv, wqkvT=wqkvT, bqkv=bqkv, wfc1=wfc1, wfc1T=wfc1T, bfc1=bfc1, wfc2=wfc2,
-                             wfc2T=wfc2T, bfc2=bfc2, wproj=self._dev(w_full, BF16), wprojT=self._dev(w_full.t(), BF16),
-                             bproj=self._dev(b_full, F32), ln1w=self._dev(blk.norm1.weight, F32),
+                             wfc2T=wfc2T, bfc2=bfc2, wproj=self._wproj_all[l], wprojT=self._wprojT_all[l],
+                             bproj=self._bproj_all[l], ln1w=self._dev(blk.norm1.weight, F32),
                              ln1b=self._dev(blk.norm1.bias, F32), ln2w=self._dev(blk.norm2.weight, F32),
                              ln2b=self._dev(blk.norm2.bias, F32)).items():
                 self._set(k, v, l)
