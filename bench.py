@@ -148,29 +148,68 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------
-def time_dominant_kernel(eng, torch, iters=24):
-    """CUDA-event timing of the dominant kernel as the step launches it: the Mlp.fc1 GEMM (+bias+GELU epilogue,
-    [T,768]x[768,3072]) -- rotating over the 12 blocks' weights/outputs so operands come from HBM, not L2."""
+# DRAM bytes (read + write) per launch of the dominant kernel from `ncu --set full` (profiles/ncu_r1c_summary.md):
+# qkv 50.8 MB, fc1-dgrad 118.2 MB, qkv-dgrad 85.5 MB, weighted by 12 / 12 / 11 launches per step.
+DOMINANT_TRAFFIC_BYTES = (12 * 50.8e6 + 12 * 118.2e6 + 11 * 85.5e6) / 35
+
+
+def time_dominant_kernel(eng, torch, rounds=3):
+    """CUDA-event timing (torch's current stream = the launching stream) of the kernel with the largest share of the
+    step, gemm2_kernel<256, EPI_BIAS> (21.6 % in profiles/launches_r1c_summary.txt): the plain 2-CTA tcgen05 GEMM that
+    runs qkv forward [T,768]x[768,2304], fc1 dgrad [T,3072]x[3072,768] and qkv dgrad [T,2304]x[2304,768] -- timed
+    on exactly those shapes in the step's 12 / 12 / 11 proportion, rotating over 4 operand sets so they come from
+    HBM / L2 like in the step.  Also times the fc1 + GELU epilogue kernel (the single most expensive launch)."""
     from apla_b200 import ops
     sh = eng.shape
     T, D, Hd, L = sh["T"], sh["D"], sh["hidden"], sh["L"]
-    x = torch.randn(T, D, device="cuda").to(torch.bfloat16)
-    ws = [(torch.randn(Hd, D, device="cuda") * 0.02).to(torch.bfloat16) for _ in range(4)]
-    hs = [torch.empty(T, Hd, device="cuda", dtype=torch.float16) for _ in range(4)]
-    gs = [torch.empty(T, Hd, device="cuda", dtype=torch.bfloat16) for _ in range(4)]
-    bias = torch.zeros(Hd, device="cuda")
-    for i in range(4):
-        ops.gemm_bias_gelu_dgelu(x, ws[i], bias, d=hs[i], g=gs[i])
+    bf = torch.bfloat16
+
+    def mats(n, k):
+        return [(torch.randn(n, k, device="cuda") * 0.02).to(bf) for _ in range(4)]
+    x_d = [torch.randn(T, D, device="cuda").to(bf) for _ in range(2)]
+    x_h = [torch.randn(T, Hd, device="cuda").to(bf) for _ in range(2)]
+    x_q = [torch.randn(T, 3 * D, device="cuda").to(bf) for _ in range(2)]
+    w_qkv, w_fc1t, w_qkvt = mats(3 * D, D), mats(D, Hd), mats(D, 3 * D)
+    o_q = [torch.empty(T, 3 * D, device="cuda", dtype=bf) for _ in range(2)]
+    o_d = [torch.empty(T, D, device="cuda", dtype=bf) for _ in range(2)]
+    bias = torch.zeros(3 * D, device="cuda")
+    plan = []      # (callable, flops) in the step's proportion
+    for i in range(L):
+        plan.append((lambda i=i: ops.gemm_bias(x_d[i % 2], w_qkv[i % 4], bias, out=o_q[i % 2]), 2.0 * T * 3 * D * D))
+        plan.append((lambda i=i: ops.gemm_dgrad(x_h[i % 2], w_fc1t[i % 4], out=o_d[i % 2]), 2.0 * T * D * Hd))
+        if i:
+            plan.append((lambda i=i: ops.gemm_dgrad(x_q[i % 2], w_qkvt[i % 4], out=o_d[i % 2]), 2.0 * T * D * 3 * D))
+    for fn, _ in plan:
+        fn()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for i in range(iters):
-        ops.gemm_bias_gelu_dgelu(x, ws[i % 4], bias, d=hs[i % 4], g=gs[i % 4])
+    for _ in range(rounds):
+        for fn, _ in plan:
+            fn()
     b.record()
     torch.cuda.synchronize()
-    sec = a.elapsed_time(b) * 1e-3 / iters
-    return dict(kernel="gemm2_kernel<256,EPI_BIAS_GELU_D> (Mlp.fc1 + GELU + saved GELU', 16448x3072x768)", us=sec * 1e6,
-                tflops=2.0 * T * D * Hd / sec / 1e12)
+    sec = a.elapsed_time(b) * 1e-3 / (rounds * len(plan))
+    flops = sum(f for _, f in plan) / len(plan)
+    dom = dict(kernel="g2::gemm2_kernel<256, EPI_BIAS> (qkv fwd / fc1 dgrad / qkv dgrad, 12:12:11)", launches=len(plan),
+               us_per_launch=sec * 1e6, flops_per_launch=flops, tflops=flops / sec / 1e12)
+    # the fc1 + GELU + saved-derivative epilogue kernel
+    ws = mats(Hd, D)
+    hs = [torch.empty(T, Hd, device="cuda", dtype=torch.float16) for _ in range(2)]
+    gs = [torch.empty(T, Hd, device="cuda", dtype=bf) for _ in range(2)]
+    b1 = torch.zeros(Hd, device="cuda")
+    for i in range(4):
+        ops.gemm_bias_gelu_dgelu(x_d[i % 2], ws[i], b1, d=hs[i % 2], g=gs[i % 2])
+    torch.cuda.synchronize()
+    a.record()
+    for i in range(24):
+        ops.gemm_bias_gelu_dgelu(x_d[i % 2], ws[i % 4], b1, d=hs[i % 2], g=gs[i % 2])
+    b.record()
+    torch.cuda.synchronize()
+    sec1 = a.elapsed_time(b) * 1e-3 / 24
+    fc1 = dict(kernel="g2::gemm2_kernel<256, EPI_BIAS_GELU_D> (Mlp.fc1 + GELU + saved GELU', 16448x3072x768)",
+               us_per_launch=sec1 * 1e6, tflops=2.0 * T * D * Hd / sec1 / 1e12)
+    return dom, fc1
 
 
 def run_gpu(args):
@@ -242,7 +281,7 @@ def run_gpu(args):
         f_fwd, f_bwd = flops_per_image(a.embed_dim, a.depth, w["patch"], w["img"], w["partial_size"], w["n_classes"])
         flops_step = (f_fwd + f_bwd) * B
         achieved = flops_step / (ms_step * 1e-3) / 1e12
-        dom = time_dominant_kernel(eng, torch)
+        dom, fc1 = time_dominant_kernel(eng, torch)
         line = dict(
             metric=METRIC, value=B * world / (ms_step * 1e-3), unit="images/s", n_gpus=world, steps=args.steps,
             warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -252,12 +291,19 @@ def run_gpu(args):
                         global_batch=B * world, batch_per_gpu=B, tokens_per_image=257, parallelism=f"dp{world}",
                         l2="per-step working set ~5 GB >> 126 MB L2 (activations of 12 blocks), no flush needed",
                         **{k: v for k, v in w.items() if k != "batch_per_gpu"}),
-            roofline=dict(bound="tensor", scope="whole step (all kernels), algorithmic FLOPs of SURVEY.md App. B",
-                          achieved=achieved, peak=peaks["tflops_sustained"], unit="TFLOP/s",
-                          frac=achieved / peaks["tflops_sustained"], frac_of_burst=achieved / peaks["tflops_burst"],
-                          peak_source=f"{peaks['source']} (sustained cuBLAS bf16; burst {peaks['tflops_burst']})",
-                          flops_per_step=flops_step, traffic=None,
-                          dominant_kernel=dict(**dom, frac_of_burst=dom["tflops"] / peaks["tflops_burst"])),
+            # dominant kernel (largest share of the step), algorithmic FLOPs 2*M*N*K per launch / live CUDA-event time;
+            # peak = measured burst cuBLAS bf16 (kernel timed alone); `step` = the whole step against the sustained peak
+            roofline=dict(bound="tensor", kernel=dom["kernel"], achieved=dom["tflops"], peak=peaks["tflops_burst"],
+                          unit="TFLOP/s", frac=dom["tflops"] / peaks["tflops_burst"],
+                          peak_source=f"{peaks['source']} MEASURED_PEAKS.json bf16_tflops (burst)",
+                          us_per_launch=dom["us_per_launch"], flops_per_launch=dom["flops_per_launch"],
+                          launches_timed=dom["launches"], traffic=DOMINANT_TRAFFIC_BYTES,
+                          traffic_note="dram read+write bytes per launch, ncu --set full (profiles/ncu_r1c_summary.md)",
+                          fc1_gelu_kernel=dict(**fc1, frac=fc1["tflops"] / peaks["tflops_burst"]),
+                          step=dict(scope="whole step (all kernels), algorithmic FLOPs of SURVEY.md App. B",
+                                    achieved=achieved, peak=peaks["tflops_sustained"], unit="TFLOP/s",
+                                    frac=achieved / peaks["tflops_sustained"],
+                                    frac_of_burst=achieved / peaks["tflops_burst"], flops_per_step=flops_step)),
             e2e=dict(value=B * world / (ms_e2e * 1e-3), unit="images/s", ms_per_step=ms_e2e,
                      h2d_bytes_per_step=images_pin.numel() * 4 + labels_pin.numel() * 8, d2h_bytes_per_step=4),
             gpu_launches=launches_per_step * args.steps, gpu_launches_per_step=launches_per_step, clocks=clocks)
