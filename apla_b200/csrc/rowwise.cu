@@ -78,13 +78,22 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld_dy, const float* 
   if (row >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
   const uint2* dyr = reinterpret_cast<const uint2*>(dy + row * ld_dy);
-  float4 v[NV], g[NV];
+  const float4* rr = dres ? reinterpret_cast<const float4*>(dres + row * ld_dres) : nullptr;
+  // all three input streams of the row are requested up front (14 x 512 B in flight per warp): the kernel is HBM-bound
+  // and the reductions below would otherwise sit between three dependent DRAM round trips
+  float4 v[NV], g[NV], r4[NV];
+  uint2 dr[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = __ldcs(xr + lane + 32 * i);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) dr[i] = __ldcs(dyr + lane + 32 * i);
+  if (rr) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) r4[i] = __ldcs(rr + lane + 32 * i);
+  }
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    v[i] = __ldcs(xr + lane + 32 * i);
-    s += v[i].x + v[i].y + v[i].z + v[i].w;
-  }
+  for (int i = 0; i < NV; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
   const float mean = warp_sum(s) * (1.f / D);
   float q = 0.f;
 #pragma unroll
@@ -96,7 +105,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld_dy, const float* 
   float sg = 0.f, sgx = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const uint2 d = __ldcs(dyr + lane + 32 * i);
+    const uint2 d = dr[i];
     const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * i);
     v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;   // xhat
     g[i] = make_float4(bf16_lo(d.x) * ww.x, bf16_hi(d.x) * ww.y, bf16_lo(d.y) * ww.z, bf16_hi(d.y) * ww.w);
@@ -104,7 +113,6 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld_dy, const float* 
     sgx += g[i].x * v[i].x + g[i].y * v[i].y + g[i].z * v[i].z + g[i].w * v[i].w;
   }
   const float mg = warp_sum(sg) * (1.f / D), mgx = warp_sum(sgx) * (1.f / D);
-  const float4* rr = dres ? reinterpret_cast<const float4*>(dres + row * ld_dres) : nullptr;
   float4* outr = reinterpret_cast<float4*>(dx + row * ld_dx);
   uint2* outb = dxb ? reinterpret_cast<uint2*>(dxb + row * ld_dxb) : nullptr;
   float* sr = srow + wib * D;
@@ -116,8 +124,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld_dy, const float* 
     o.z = rstd * (g[i].z - mg - v[i].z * mgx);
     o.w = rstd * (g[i].w - mg - v[i].w * mgx);
     if (rr) {
-      const float4 r4 = __ldcs(rr + lane + 32 * i);
-      o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+      o.x += r4[i].x; o.y += r4[i].y; o.z += r4[i].z; o.w += r4[i].w;
     }
     outr[lane + 32 * i] = o;
     if (outb || sub) {
