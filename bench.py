@@ -82,7 +82,7 @@ class ClockSampler:
                     self.reasons.add(f[2])
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02)
 
     def start(self):
         self._thread = threading.Thread(target=self._loop, daemon=True)
@@ -148,14 +148,14 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------
-# DRAM bytes (read + write) per launch of the dominant kernel from `ncu --set full` (profiles/ncu_r1c_summary.md):
-# qkv 50.8 MB, fc1-dgrad 118.2 MB, qkv-dgrad 85.5 MB, weighted by 12 / 12 / 11 launches per step.
-DOMINANT_TRAFFIC_BYTES = (12 * 50.8e6 + 12 * 118.2e6 + 11 * 85.5e6) / 35
+# DRAM bytes (read + write) per launch of the dominant kernel from `ncu --set full` (profiles/ncu_r1d_summary.md):
+# qkv 50.0 MB, fc1-dgrad 119.1 MB, qkv-dgrad 86.6 MB, weighted by 12 / 12 / 11 launches per step.
+DOMINANT_TRAFFIC_BYTES = (12 * 50.0e6 + 12 * 119.1e6 + 11 * 86.6e6) / 35
 
 
 def time_dominant_kernel(eng, torch, rounds=3):
     """CUDA-event timing (torch's current stream = the launching stream) of the kernel with the largest share of the
-    step, gemm2_kernel<256, EPI_BIAS> (21.6 % in profiles/launches_r1c_summary.txt): the plain 2-CTA tcgen05 GEMM that
+    step, gemm2_kernel<256, EPI_BIAS> (21.6 % in profiles/launches_r1d_summary.txt): the plain 2-CTA tcgen05 GEMM that
     runs qkv forward [T,768]x[768,2304], fc1 dgrad [T,3072]x[3072,768] and qkv dgrad [T,2304]x[2304,768] -- timed
     on exactly those shapes in the step's 12 / 12 / 11 proportion, rotating over 4 operand sets so they come from
     HBM / L2 like in the step.  Also times the fc1 + GELU epilogue kernel (the single most expensive launch)."""
@@ -298,7 +298,7 @@ def run_gpu(args):
                           peak_source=f"{peaks['source']} MEASURED_PEAKS.json bf16_tflops (burst)",
                           us_per_launch=dom["us_per_launch"], flops_per_launch=dom["flops_per_launch"],
                           launches_timed=dom["launches"], traffic=DOMINANT_TRAFFIC_BYTES,
-                          traffic_note="dram read+write bytes per launch, ncu --set full (profiles/ncu_r1c_summary.md)",
+                          traffic_note="dram read+write bytes per launch, ncu --set full (profiles/ncu_r1d_summary.md)",
                           fc1_gelu_kernel=dict(**fc1, frac=fc1["tflops"] / peaks["tflops_burst"]),
                           step=dict(scope="whole step (all kernels), algorithmic FLOPs of SURVEY.md App. B",
                                     achieved=achieved, peak=peaks["tflops_sustained"], unit="TFLOP/s",
