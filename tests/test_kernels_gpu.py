@@ -225,7 +225,8 @@ def _attn_ref(qkv, seqlens, H, scale):
     return torch.cat(outs, 0)
 
 
-@pytest.mark.parametrize("B,N,H", [(2, 257, 12), (3, 197, 6), (1, 1370, 12), (4, 50, 16), (2, 64, 2), (5, 17, 2)])
+@pytest.mark.parametrize("B,N,H", [(2, 257, 12), (30, 257, 12), (3, 197, 6), (1, 1370, 12), (4, 50, 16), (2, 64, 2), (5, 17, 2),
+                                   (2, 272, 2)])
 def test_attention_dense(B, N, H):
     ops = _cuda()
     g = torch.Generator(device="cuda").manual_seed(B * N + H)
