@@ -33,6 +33,12 @@ struct Engine {
   // shape
   int B = 0, N = 0, D = 0, H = 0, L = 0, hidden = 0, C = 0, P = 0, patch = 0, img = 0, kpad = 0;
   int r = 0, r_pad = 0, full_rows = 0;  // full_rows: partial_size == dim handled through rowmap on the dense dY
+  // Only the CLS token of the last block's output reaches the head (forward_features returns norm(x)[:, 0],
+  // src/utils/transformers/vit.py:417-419; Classifier.fc models.py:87).  Everything in the last block that is
+  // per-token -- the projection, LayerNorm 2, the whole MLP branch and, on the way back, their input gradients -- is
+  // therefore evaluated on the B CLS rows only (row stride N*D); all other rows of those tensors are dead values in
+  // the forward pass and exact zeros in the backward pass.  Attention itself still needs every token's K and V.
+  int cls_last = 1;
   float eps = 1e-6f, scale = 0.125f;
   std::vector<BlockPtrs> blk;
   std::map<std::string, void*> g;  // global buffers by name
@@ -117,11 +123,15 @@ static int engine_forward(Engine* e, const float* images, const int64_t* labels,
     if (int rc = gemm_tn(EPI_BIAS, ln_out, b.wqkv, T, 3 * D, D, D, D, b.qkv, nullptr, b.bqkv, nullptr, nullptr, 3 * D, s, 0))
       return rc;
     if (int rc = attn_fwd(b.qkv, b.ao, b.lse, nullptr, B, N, T, e->H, e->scale, s)) return rc;
-    if (int rc = gemm_tn(EPI_RESID, b.ao, b.wproj, T, D, D, D, D, x_mid, nullptr, b.bproj, b.g1, x_in, D, s, 0)) return rc;
-    if (int rc = layernorm_fwd(x_mid, D, b.ln2w, b.ln2b, ln_out, D, T, D, e->eps, s)) return rc;
-    if (int rc = gemm_tn(EPI_BIAS_GELU_D, ln_out, b.wfc1, T, Hd, D, D, D, b.hpre, gelu_out, b.bfc1, nullptr, nullptr, Hd, s, 0))
+    // rows / row strides of the per-token tail of the block: every token, or the CLS rows of the last block
+    const bool cls = e->cls_last && l == L - 1;
+    const int R = cls ? B : T;
+    const int sD = cls ? N * D : D, sH = cls ? N * Hd : Hd;
+    if (int rc = gemm_tn(EPI_RESID, b.ao, b.wproj, R, D, D, sD, D, x_mid, nullptr, b.bproj, b.g1, x_in, sD, s, 0)) return rc;
+    if (int rc = layernorm_fwd(x_mid, sD, b.ln2w, b.ln2b, ln_out, sD, R, D, e->eps, s)) return rc;
+    if (int rc = gemm_tn(EPI_BIAS_GELU_D, ln_out, b.wfc1, R, Hd, D, sD, D, b.hpre, gelu_out, b.bfc1, nullptr, nullptr, sH, s, 0))
       return rc;
-    if (int rc = gemm_tn(EPI_RESID, gelu_out, b.wfc2, T, D, Hd, Hd, Hd, x_out, nullptr, b.bfc2, b.g2, x_mid, D, s, 0))
+    if (int rc = gemm_tn(EPI_RESID, gelu_out, b.wfc2, R, D, Hd, sH, Hd, x_out, nullptr, b.bfc2, b.g2, x_mid, sD, s, 0))
       return rc;
   }
 
@@ -177,14 +187,20 @@ static int engine_backward(Engine* e, int l_from, int l_to, cudaStream_t s) {
     const BlockPtrs& b = e->blk[l];
     const float* x_in = xs + size_t(2 * l) * TD;
     const float* x_mid = xs + size_t(2 * l + 1) * TD;
-    // MLP branch: dxb holds bf16(gamma2 * dx_out); hpre holds gelu'(fc1 pre-activation) in fp16
-    if (int rc = gemm_tn(EPI_MUL_F16, dxb, b.wfc2T, T, Hd, D, D, D, dH, nullptr, nullptr, nullptr, b.hpre, Hd, s, 0))
+    // MLP branch: dxb holds bf16(gamma2 * dx_out); hpre holds gelu'(fc1 pre-activation) in fp16.  In the last block only
+    // the CLS rows of dx_out are non-zero (see Engine::cls_last): its MLP input gradients and LayerNorm-2 backward run on
+    // those B rows; dx / dxb / dsub of all other rows stay the zeros they were initialised with.
+    const bool cls = e->cls_last && l == L - 1;
+    const int R = cls ? B : T;
+    const int sD = cls ? N * D : D, sH = cls ? N * Hd : Hd;
+    if (int rc = gemm_tn(EPI_MUL_F16, dxb, b.wfc2T, R, Hd, D, sD, D, dH, nullptr, nullptr, nullptr, b.hpre, sH, s, 0))
       return rc;
-    if (int rc = gemm_tn(EPI_BIAS, dH, b.wfc1T, T, D, Hd, Hd, Hd, dln, nullptr, nullptr, nullptr, nullptr, D, s, 0))
+    if (int rc = gemm_tn(EPI_BIAS, dH, b.wfc1T, R, D, Hd, sH, Hd, dln, nullptr, nullptr, nullptr, nullptr, sD, s, 0))
       return rc;
+    if (cls && dsub) APLA_CUDA(cudaMemsetAsync(dsub, 0, size_t(T) * e->r_pad * 2, s));
     // dx_mid = dx_out + LN2'(dln); dxb = bf16(gamma1 * dx_mid); dsub = its APLA columns
-    if (int rc = layernorm_bwd(dln, D, x_mid, D, b.ln2w, dx, D, dx, D, dxb, D, b.g1, dsub, e->r_pad,
-                               idx + size_t(l) * r, r, e->r_pad, T, D, e->eps, s))
+    if (int rc = layernorm_bwd(dln, sD, x_mid, sD, b.ln2w, dx, sD, dx, sD, dxb, sD, b.g1, dsub,
+                               cls ? int64_t(N) * e->r_pad : e->r_pad, idx + size_t(l) * r, r, e->r_pad, R, D, e->eps, s))
       return rc;
     // APLA weight gradient: only the trainable rows of the projection (appla_attn.py:64,70-74)
     float* dW1 = grads + ar.w1 + size_t(l) * r * D;
@@ -295,6 +311,17 @@ int apla_engine_set_ptr(apla_engine_t h, const char* name, int block, void* p) {
   SETP(lse)
 #undef SETP
   set_error("apla_engine_set_ptr: unknown block pointer '%s'", name);
+  return 1;
+}
+
+int apla_engine_set_option(apla_engine_t h, const char* name, int value) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  APLA_CHECK(e != nullptr && name != nullptr, "apla_engine_set_option: null handle or name");
+  if (std::string(name) == "cls_only_last_block") {
+    e->cls_last = value ? 1 : 0;
+    return 0;
+  }
+  set_error("apla_engine_set_option: unknown option '%s'", name);
   return 1;
 }
 

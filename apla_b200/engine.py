@@ -49,8 +49,11 @@ def interpolate_pos_table(pos_embed: torch.Tensor, npatch: int) -> torch.Tensor:
 class FineTuneEngine:
     def __init__(self, model: nn.Module, batch_size: int, img_size: int, device="cuda", lr: float = 3e-5,
                  weight_decay: float = 1e-5, clip: float = 1.0, betas=(0.9, 0.999), adam_eps: float = 1e-8,
-                 process_group=None):
+                 process_group=None, cls_only_last_block: bool = True):
         require_device()
+        # Only norm(x)[:, 0] of the last block reaches the head (vit.py:417-419): its projection, LayerNorm 2, MLP and
+        # their input gradients run on the CLS rows only.  False = every token (identical results, for A/B checks).
+        self.cls_only_last_block = bool(cls_only_last_block)
         self.device = torch.device(device)
         self.model = model
         self.lr, self.wd, self.clip, self.betas, self.adam_eps = lr, weight_decay, clip, betas, adam_eps
@@ -104,6 +107,7 @@ class FineTuneEngine:
                                                      eps, scale)
         if not self._handle:
             raise RuntimeError("apla_engine_create failed: " + LIB.last_error())
+        LIB.call("apla_engine_set_option", self._handle, b"cls_only_last_block", int(self.cls_only_last_block))
 
         # ---- embedding ----
         wpe = torch.zeros(D, kpad, dtype=F32)

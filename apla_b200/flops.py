@@ -3,12 +3,20 @@
 the r APLA rows (2*r*D per token) and the head; block 0's attention / qkv / proj input gradients are pruned."""
 
 
-def flops_per_image(D: int, L: int, patch: int, img: int, r: int, n_classes: int):
-    """-> (forward, backward) FLOPs per image."""
+def flops_per_image(D: int, L: int, patch: int, img: int, r: int, n_classes: int, cls_only_last_block: bool = False):
+    """-> (forward, backward) FLOPs per image.
+
+    cls_only_last_block: the engine evaluates the per-token tail of the last block (projection 2*D*D, MLP 16*D*D per
+    token forward; MLP input gradients 16*D*D per token backward) on the CLS token only -- the other N-1 tokens' values
+    never reach the head.  True = count what is executed (the conservative numerator for a roofline fraction); False =
+    the reference's dense algorithm, SURVEY.md Appendix B."""
     P = (img // patch) ** 2
     N = P + 1
     lin = 24 * D * D
     att = 4 * N * D
     fwd = 2 * 3 * patch * patch * D * P + L * N * (lin + att) + 2 * D * n_classes
     bwd = (L - 1) * N * (lin + 2.5 * att + 2 * r * D) + N * (16 * D * D + 2 * r * D) + 2 * (2 * D * n_classes)
+    if cls_only_last_block:
+        fwd -= (N - 1) * 18 * D * D
+        bwd -= (N - 1) * 16 * D * D
     return float(fwd), float(bwd)

@@ -279,7 +279,10 @@ def run_gpu(args):
         peaks = load_peaks()
         a = ARCHS[w["arch"]]
         f_fwd, f_bwd = flops_per_image(a.embed_dim, a.depth, w["patch"], w["img"], w["partial_size"], w["n_classes"])
-        flops_step = (f_fwd + f_bwd) * B
+        flops_step_ref = (f_fwd + f_bwd) * B                      # the reference's dense algorithm
+        e_fwd, e_bwd = flops_per_image(a.embed_dim, a.depth, w["patch"], w["img"], w["partial_size"], w["n_classes"],
+                                       cls_only_last_block=eng.cls_only_last_block)
+        flops_step = (e_fwd + e_bwd) * B                          # what this engine executes (last block: CLS rows)
         achieved = flops_step / (ms_step * 1e-3) / 1e12
         dom, fc1 = time_dominant_kernel(eng, torch)
         line = dict(
@@ -300,10 +303,15 @@ def run_gpu(args):
                           launches_timed=dom["launches"], traffic=DOMINANT_TRAFFIC_BYTES,
                           traffic_note="dram read+write bytes per launch, ncu --set full (profiles/ncu_r1d_summary.md)",
                           fc1_gelu_kernel=dict(**fc1, frac=fc1["tflops"] / peaks["tflops_burst"]),
-                          step=dict(scope="whole step (all kernels), algorithmic FLOPs of SURVEY.md App. B",
+                          step=dict(scope="whole step (all kernels); EXECUTED algorithmic FLOPs: SURVEY.md App. B minus the "
+                                          "last block's per-token work on non-CLS tokens, which the engine proves dead "
+                                          "and does not run (DESIGN.md section 5)",
                                     achieved=achieved, peak=peaks["tflops_sustained"], unit="TFLOP/s",
                                     frac=achieved / peaks["tflops_sustained"],
-                                    frac_of_burst=achieved / peaks["tflops_burst"], flops_per_step=flops_step)),
+                                    frac_of_burst=achieved / peaks["tflops_burst"], flops_per_step=flops_step,
+                                    flops_per_step_reference_dense=flops_step_ref,
+                                    frac_reference_dense_flops=flops_step_ref / (ms_step * 1e-3) / 1e12
+                                    / peaks["tflops_sustained"])),
             e2e=dict(value=B * world / (ms_e2e * 1e-3), unit="images/s", ms_per_step=ms_e2e,
                      h2d_bytes_per_step=images_pin.numel() * 4 + labels_pin.numel() * 8, d2h_bytes_per_step=4),
             gpu_launches=launches_per_step * args.steps, gpu_launches_per_step=launches_per_step, clocks=clocks)

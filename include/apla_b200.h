@@ -142,6 +142,10 @@ apla_engine_t apla_engine_create(int B, int N, int D, int H, int L, int hidden, 
                                  int r, int r_pad, int full_rows, float eps, float scale);
 void apla_engine_destroy(apla_engine_t e);
 int apla_engine_set_ptr(apla_engine_t e, const char* name, int block, void* p);
+/* Options (default in brackets): "cls_only_last_block" [1] -- evaluate the per-token tail of the LAST block (projection,
+ * LayerNorm 2, MLP and their input gradients) on the CLS rows only, because only norm(x)[:, 0] reaches the head
+ * (vit.py:417-419, models.py:87); 0 = every token, bit-identical logits / loss / gradients, for A/B checks. */
+int apla_engine_set_option(apla_engine_t e, const char* name, int value);
 /* Trainable arena layout (fp32): [proj_weight1 x L | fc.weight | proj_bias1 x L | fc.bias]; the first
  * apla_engine_arena_decay_size() elements are weight-decayed (src/defaults/wrappers.py:205-221). */
 int64_t apla_engine_arena_size(apla_engine_t e);

@@ -85,6 +85,32 @@ def test_engine_vs_live_oracle_other_batch():
     assert cosine(ours, theirs) >= 0.999
 
 
+def test_cls_only_last_block_is_exact():
+    """The last block's per-token tail evaluated on the CLS rows only (default) vs on every token: same logits, loss,
+    gradients and updated parameters (only dead values / exact zeros are skipped)."""
+    from apla_b200.config import AplaConfig
+    from apla_b200.hostvit import VitArch, build_classifier
+    outs = []
+    for cls_only in (True, False):
+        for r in (16, 128):
+            model = build_classifier(VitArch(128, 3, 2), img_size=224, patch_size=14, n_classes=37,
+                                     apla_config=AplaConfig(r), seed=0)
+            eng = _engine(model, 6, 224, cls_only_last_block=cls_only)
+            g = torch.Generator().manual_seed(4)
+            images = torch.randn(6, 3, 224, 224, generator=g).cuda()
+            labels = torch.randint(0, 37, (6,), generator=g).cuda()
+            for _ in range(2):
+                eng.step(images, labels)
+            torch.cuda.synchronize()
+            outs.append((eng.logits.clone(), eng.loss.clone(), eng.grads.clone(), eng.params.clone()))
+    n = len(outs) // 2
+    for a, b in zip(outs[:n], outs[n:]):
+        assert torch.equal(a[0], b[0])                                   # logits bit-identical
+        assert abs(float(a[1]) - float(b[1])) <= 1e-6 * abs(float(b[1]))
+        assert float((a[2] - b[2]).norm() / b[2].norm()) < 1e-5          # only the wgrad's fp32 atomics differ
+        assert float((a[3] - b[3]).norm() / b[3].norm()) < 1e-6
+
+
 def test_sync_to_model_roundtrip():
     model, meta, arr = build_case("tiny_r16")
     m = meta["meta"]
