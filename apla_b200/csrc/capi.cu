@@ -92,6 +92,14 @@ int apla_attn_bwd(const void* qkv, const void* out, const void* dout, const floa
   return attn_bwd(qkv, out, dout, lse, delta, dqkv, cu_seqlens, num_seqs, max_seqlen, total_tokens, H, scale, S(stream));
 }
 
+int apla_attn_cls_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, apla_stream_t stream) {
+  return attn_cls_fwd(qkv, out, lse, B, N, H, scale, S(stream));
+}
+int apla_attn_cls_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int N,
+                      int H, float scale, apla_stream_t stream) {
+  return attn_cls_bwd(qkv, out, dout, lse, dqkv, B, N, H, scale, S(stream));
+}
+
 int apla_patchify(const float* images, void* patches, int B, int Simg, int patch, int kpad, apla_stream_t stream) {
   return patchify(images, patches, B, Simg, patch, kpad, S(stream));
 }

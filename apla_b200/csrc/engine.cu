@@ -38,7 +38,7 @@ struct Engine {
   // per-token -- the projection, LayerNorm 2, the whole MLP branch and, on the way back, their input gradients -- is
   // therefore evaluated on the B CLS rows only (row stride N*D); all other rows of those tensors are dead values in
   // the forward pass and exact zeros in the backward pass.  Attention itself still needs every token's K and V.
-  int cls_last = 1;
+  int cls_last = 2;   // 0 = every token everywhere, 1 = CLS-only per-token tail, 2 = also CLS-only attention (default)
   float eps = 1e-6f, scale = 0.125f;
   std::vector<BlockPtrs> blk;
   std::map<std::string, void*> g;  // global buffers by name
@@ -122,9 +122,13 @@ static int engine_forward(Engine* e, const float* images, const int64_t* labels,
     if (int rc = layernorm_fwd(x_in, D, b.ln1w, b.ln1b, ln_out, D, T, D, e->eps, s)) return rc;
     if (int rc = gemm_tn(EPI_BIAS, ln_out, b.wqkv, T, 3 * D, D, D, D, b.qkv, nullptr, b.bqkv, nullptr, nullptr, 3 * D, s, 0))
       return rc;
-    if (int rc = attn_fwd(b.qkv, b.ao, b.lse, nullptr, B, N, T, e->H, e->scale, s)) return rc;
     // rows / row strides of the per-token tail of the block: every token, or the CLS rows of the last block
     const bool cls = e->cls_last && l == L - 1;
+    if (cls && e->cls_last >= 2) {   // one query row per (image, head); the other rows of ao stay zero
+      if (int rc = attn_cls_fwd(b.qkv, b.ao, b.lse, B, N, e->H, e->scale, s)) return rc;
+    } else {
+      if (int rc = attn_fwd(b.qkv, b.ao, b.lse, nullptr, B, N, T, e->H, e->scale, s)) return rc;
+    }
     const int R = cls ? B : T;
     const int sD = cls ? N * D : D, sH = cls ? N * Hd : Hd;
     if (int rc = gemm_tn(EPI_RESID, b.ao, b.wproj, R, D, D, sD, D, x_mid, nullptr, b.bproj, b.g1, x_in, sD, s, 0)) return rc;
@@ -214,12 +218,19 @@ static int engine_backward(Engine* e, int l_from, int l_to, cudaStream_t s) {
     }
     if (l == 0) break;  // nothing trainable upstream of block 0's attention
     void* dO = e->get<void>("dO");
-    // dO = dY Wproj, and delta = rowsum(dO * O) per (token, head) from the same epilogue
-    if (int rc = gemm_tn(EPI_DELTA, dxb, b.wprojT, T, D, D, D, D, dO, e->get<float>("delta"), nullptr, nullptr, b.ao, D, s, 0))
-      return rc;
-    if (int rc = attn_bwd(b.qkv, nullptr, dO, b.lse, e->get<float>("delta"), e->get<void>("dqkv"), nullptr, B, N, T, e->H,
-                          e->scale, s))
-      return rc;
+    if (cls && e->cls_last >= 2) {
+      // last block: dO and dQ exist for the CLS rows only; dK / dV of every key come from that one row
+      if (int rc = gemm_tn(EPI_BIAS, dxb, b.wprojT, B, D, D, N * D, D, dO, nullptr, nullptr, nullptr, nullptr, N * D, s, 0))
+        return rc;
+      if (int rc = attn_cls_bwd(b.qkv, b.ao, dO, b.lse, e->get<void>("dqkv"), B, N, e->H, e->scale, s)) return rc;
+    } else {
+      // dO = dY Wproj, and delta = rowsum(dO * O) per (token, head) from the same epilogue
+      if (int rc = gemm_tn(EPI_DELTA, dxb, b.wprojT, T, D, D, D, D, dO, e->get<float>("delta"), nullptr, nullptr, b.ao, D, s, 0))
+        return rc;
+      if (int rc = attn_bwd(b.qkv, nullptr, dO, b.lse, e->get<float>("delta"), e->get<void>("dqkv"), nullptr, B, N, T, e->H,
+                            e->scale, s))
+        return rc;
+    }
     if (int rc = gemm_tn(EPI_BIAS, e->get<void>("dqkv"), b.wqkvT, T, D, 3 * D, 3 * D, 3 * D, dln, nullptr, nullptr, nullptr,
                          nullptr, D, s, 0))
       return rc;
@@ -318,7 +329,7 @@ int apla_engine_set_option(apla_engine_t h, const char* name, int value) {
   Engine* e = reinterpret_cast<Engine*>(h);
   APLA_CHECK(e != nullptr && name != nullptr, "apla_engine_set_option: null handle or name");
   if (std::string(name) == "cls_only_last_block") {
-    e->cls_last = value ? 1 : 0;
+    e->cls_last = value < 0 ? 0 : (value > 2 ? 2 : value);
     return 0;
   }
   set_error("apla_engine_set_option: unknown option '%s'", name);

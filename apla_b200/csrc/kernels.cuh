@@ -42,6 +42,11 @@ int attn_bwd(const void* qkv, const void* out, const void* dout, const float* ls
              const int* cu_seqlens, int num_seqs, int max_seqlen, int total_tokens, int H, float scale,
              cudaStream_t stream);
 
+// attention_cls.cu: the last block's attention for the CLS query only (rows b*N of out / lse / dout; dqkv dense)
+int attn_cls_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t stream);
+int attn_cls_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int N, int H,
+                 float scale, cudaStream_t stream);
+
 // rowwise.cu
 int layernorm_fwd(const float* x, int64_t ldx, const float* w, const float* b, void* y, int64_t ldy, int rows, int D,
                   float eps, cudaStream_t stream);

@@ -53,7 +53,7 @@ class FineTuneEngine:
         require_device()
         # Only norm(x)[:, 0] of the last block reaches the head (vit.py:417-419): its projection, LayerNorm 2, MLP and
         # their input gradients run on the CLS rows only.  False = every token (identical results, for A/B checks).
-        self.cls_only_last_block = bool(cls_only_last_block)
+        self.cls_only_last_block = 2 if cls_only_last_block is True else int(cls_only_last_block)   # 1: tail only
         self.device = torch.device(device)
         self.model = model
         self.lr, self.wd, self.clip, self.betas, self.adam_eps = lr, weight_decay, clip, betas, adam_eps
@@ -194,7 +194,7 @@ class FineTuneEngine:
             self._set("g1", self._dev(g1, F32) if g1 is not None else None, l)
             self._set("g2", self._dev(g2, F32) if g2 is not None else None, l)
             self._set("qkv", self._new(T, 3 * D), l)
-            self._set("ao", self._new(T, D), l)
+            self._set("ao", self._new(T, D, zero=True), l)   # last block: only its CLS rows are ever written
             self._set("hpre", self._new(T, hidden, dtype=torch.float16), l)
             self._set("lse", self._new(T, H, dtype=F32), l)
 

@@ -216,3 +216,28 @@ def attn_bwd(qkv, out, dout, lse, H: int, scale: float, num_seqs: int, max_seqle
     LIB.call("apla_attn_bwd", ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqkv), ptr(cu_seqlens),
              num_seqs, max_seqlen, T, H, scale, stream())
     return dqkv
+
+
+def attn_cls_fwd(qkv, H: int, scale: float, B: int, N: int, out=None, lse=None):
+    """Row b*N of the attention output / lse only (the CLS query of each of the B sequences of N tokens)."""
+    require_device()
+    _chk(qkv, BF16, "qkv", 2)
+    T = qkv.shape[0]
+    assert T == B * N and qkv.shape[1] == 3 * H * 64 and qkv.is_contiguous()
+    if out is None:
+        out = torch.zeros(T, H * 64, device=qkv.device, dtype=BF16)
+    if lse is None:
+        lse = torch.zeros(T, H, device=qkv.device, dtype=F32)
+    LIB.call("apla_attn_cls_fwd", ptr(qkv), ptr(out), ptr(lse), B, N, H, scale, stream())
+    return out, lse
+
+
+def attn_cls_bwd(qkv, out, dout, lse, H: int, scale: float, B: int, N: int, dqkv=None):
+    """dqkv for a dout that is non-zero on the CLS rows only (rows b*N of out / dout / lse are read)."""
+    require_device()
+    _chk(qkv, BF16, "qkv", 2); _chk(out, BF16, "out", 2); _chk(dout, BF16, "dout", 2); _chk(lse, F32, "lse", 2)
+    assert qkv.shape[0] == B * N and qkv.is_contiguous() and out.is_contiguous() and dout.is_contiguous()
+    if dqkv is None:
+        dqkv = torch.empty_like(qkv)
+    LIB.call("apla_attn_cls_bwd", ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), B, N, H, scale, stream())
+    return dqkv

@@ -281,7 +281,7 @@ def run_gpu(args):
         f_fwd, f_bwd = flops_per_image(a.embed_dim, a.depth, w["patch"], w["img"], w["partial_size"], w["n_classes"])
         flops_step_ref = (f_fwd + f_bwd) * B                      # the reference's dense algorithm
         e_fwd, e_bwd = flops_per_image(a.embed_dim, a.depth, w["patch"], w["img"], w["partial_size"], w["n_classes"],
-                                       cls_only_last_block=eng.cls_only_last_block)
+                                       cls_only_last_block=int(eng.cls_only_last_block))
         flops_step = (e_fwd + e_bwd) * B                          # what this engine executes (last block: CLS rows)
         achieved = flops_step / (ms_step * 1e-3) / 1e12
         dom, fc1 = time_dominant_kernel(eng, torch)

@@ -104,6 +104,14 @@ int apla_attn_bwd(const void* qkv, const void* out, const void* dout, const floa
                   const int32_t* cu_seqlens, int num_seqs, int max_seqlen, int total_tokens, int H, float scale,
                   apla_stream_t stream);
 
+/* Attention of the LAST block for the CLS query only (dense batch of B sequences of N tokens): only norm(x)[:, 0]
+ * reaches the classifier (vit.py:417-419, models.py:87), so only row b*N of out / lse is produced, and backward takes
+ * the gradient of that row alone: dqkv gets dK / dV of every key, dQ of the CLS rows and zeros for every other dQ row --
+ * exactly what apla_attn_fwd / apla_attn_bwd return for those rows and for a dout that is zero elsewhere. */
+int apla_attn_cls_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, apla_stream_t stream);
+int apla_attn_cls_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int N,
+                      int H, float scale, apla_stream_t stream);
+
 /* --- step ends ------------------------------------------------------------------------------------------ */
 /* patches_bf16[B*P, kpad] from images_f32[B,3,S,S], k = (c, py, px): PatchEmbed conv as a GEMM, vit.py:302-306. */
 int apla_patchify(const float* images, void* patches, int B, int S, int patch, int kpad, apla_stream_t stream);
@@ -142,9 +150,10 @@ apla_engine_t apla_engine_create(int B, int N, int D, int H, int L, int hidden, 
                                  int r, int r_pad, int full_rows, float eps, float scale);
 void apla_engine_destroy(apla_engine_t e);
 int apla_engine_set_ptr(apla_engine_t e, const char* name, int block, void* p);
-/* Options (default in brackets): "cls_only_last_block" [1] -- evaluate the per-token tail of the LAST block (projection,
- * LayerNorm 2, MLP and their input gradients) on the CLS rows only, because only norm(x)[:, 0] reaches the head
- * (vit.py:417-419, models.py:87); 0 = every token, bit-identical logits / loss / gradients, for A/B checks. */
+/* Options (default in brackets): "cls_only_last_block" [2] -- evaluate the per-token tail of the LAST block (projection,
+ * LayerNorm 2, MLP and their input gradients; value >= 1) and its attention (value 2: apla_attn_cls_*) for the CLS
+ * rows only, because only norm(x)[:, 0] reaches the head (vit.py:417-419, models.py:87); 0 = every token.  Values 0 and
+ * 1 give bit-identical logits / loss; 2 replaces bf16 tensor-core attention of that row by fp32 arithmetic. */
 int apla_engine_set_option(apla_engine_t e, const char* name, int value);
 /* Trainable arena layout (fp32): [proj_weight1 x L | fc.weight | proj_bias1 x L | fc.bias]; the first
  * apla_engine_arena_decay_size() elements are weight-decayed (src/defaults/wrappers.py:205-221). */

@@ -245,6 +245,32 @@ def test_attention_dense(B, N, H):
         assert rel(dqkv[:, part].float(), q32.grad[:, part]) < 1.2e-2, name
 
 
+@pytest.mark.parametrize("B,N,H", [(3, 257, 12), (2, 197, 6), (2, 1370, 2), (4, 50, 4)])
+def test_attention_cls_only(B, N, H):
+    """Last-block attention for the CLS query only == the dense kernels' CLS rows, and == their dqkv for a dout that is
+    zero on every other row (fp32 torch reference)."""
+    ops = _cuda()
+    g = torch.Generator(device="cuda").manual_seed(B + N + H)
+    D = H * 64
+    qkv = bf(torch.randn(B * N, 3 * D, device="cuda", generator=g))
+    scale = 0.125
+    out, lse = ops.attn_cls_fwd(qkv, H, scale, B, N)
+    q32 = qkv.float().requires_grad_(True)
+    ref = _attn_ref(q32, [N] * B, H, scale)
+    cls = torch.arange(B, device="cuda") * N
+    assert rel(out[cls].float(), ref[cls]) < 6e-3
+    assert float(out.float().abs().sum() - out[cls].float().abs().sum()) == 0.0      # other rows untouched (zero)
+    dout = torch.zeros(B * N, D, device="cuda", dtype=torch.bfloat16)
+    dout[cls] = bf(torch.randn(B, D, device="cuda", generator=g))
+    ref.backward(dout.float())
+    dqkv = ops.attn_cls_bwd(qkv, out, dout, lse, H, scale, B, N)
+    for part, name in ((slice(0, D), "dq"), (slice(D, 2 * D), "dk"), (slice(2 * D, 3 * D), "dv")):
+        assert rel(dqkv[:, part].float(), q32.grad[:, part]) < 1e-2, name
+    mask = torch.ones(B * N, dtype=torch.bool, device="cuda")
+    mask[cls] = False
+    assert float(dqkv[mask][:, :D].float().abs().max()) == 0.0                          # dQ of non-CLS rows: exact zeros
+
+
 def test_attention_varlen():
     ops = _cuda()
     g = torch.Generator(device="cuda").manual_seed(5)
