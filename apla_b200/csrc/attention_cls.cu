@@ -32,71 +32,77 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
   return r;
 }
 
-// dot of a 64-element bf16 row (128 contiguous bytes in global memory) with 64 floats in shared memory
-__device__ __forceinline__ float dot64(const __nv_bfloat16* __restrict__ row, const float* __restrict__ v) {
-  const uint4* r4 = reinterpret_cast<const uint4*>(row);
+// Thread layout of both kernels: 8 consecutive lanes share one key -- lane `sub` owns the 16-byte piece (8 head dims) of
+// its K / V row, so every 128-bit load / store instruction of a warp covers 4 whole 128-byte rows -- and the 32 groups of
+// 8 lanes walk the keys j = group, group + 32, ...  Dot products are 8 FMAs + 3 shuffles.
+__device__ __forceinline__ void unpack8(const uint4 x, float (&f)[8]) {
+  f[0] = bf16_lo(x.x); f[1] = bf16_hi(x.x); f[2] = bf16_lo(x.y); f[3] = bf16_hi(x.y);
+  f[4] = bf16_lo(x.z); f[5] = bf16_hi(x.z); f[6] = bf16_lo(x.w); f[7] = bf16_hi(x.w);
+}
+__device__ __forceinline__ float dot8_group(const float (&a)[8], const float (&b)[8]) {
   float acc = 0.f;
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const uint4 x = __ldg(r4 + u);
-    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      acc = fmaf(bf16_lo(w[t]), v[8 * u + 2 * t], acc);
-      acc = fmaf(bf16_hi(w[t]), v[8 * u + 2 * t + 1], acc);
-    }
-  }
+  for (int i = 0; i < 8; ++i) acc = fmaf(a[i], b[i], acc);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
   return acc;
 }
 
 // out[b*N, h*64 ..] = softmax(scale * q_cls K^T) V ; lse[b*N, h] = log sum exp(scale * s)
 __global__ void __launch_bounds__(kThreads)
 attn_cls_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N,
-                    int pn, int H, float scale) {
-  extern __shared__ float sm[];          // p[pn] (pn = max(N, 512): reused for the [8][64] partial outputs) | q[64] | red[8]
+                    int H, float scale) {
+  extern __shared__ float sm[];          // p[N] | o[64] | red[8]
   float* p = sm;
-  float* q = p + pn;
-  float* red = q + 64;
+  float* osum = p + N;
+  float* red = osum + 64;
   const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   const int D = H * 64;
   const size_t row0 = size_t(b) * N;
   const __nv_bfloat16* base = qkv + row0 * (3 * D) + h * 64;
-  if (threadIdx.x < 64) q[threadIdx.x] = __bfloat162float(base[threadIdx.x]) * (scale * LOG2E);
-  __syncthreads();
-  float mx = -INFINITY;
-  for (int j = threadIdx.x; j < N; j += kThreads) {
-    const float s = dot64(base + size_t(j) * (3 * D) + D, q);      // log2-domain score
-    p[j] = s;
-    mx = fmaxf(mx, s);
-  }
-  mx = block_reduce(mx, red, true);
-  float sum = 0.f;
-  for (int j = threadIdx.x; j < N; j += kThreads) {
-    const float e = exp2f(p[j] - mx);
-    p[j] = e;
-    sum += e;
-  }
-  const float l = block_reduce(sum, red, false);                    // (also orders the p[] writes before the reads below)
-  // O[2 dp .. 2 dp + 1] over the keys part, part + 8, ...: 32 column pairs x 8 key slices
-  const int dp = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  float o0 = 0.f, o1 = 0.f;
-  for (int j = slice; j < N; j += kThreads / 32) {
-    const uint32_t vv = __ldg(reinterpret_cast<const uint32_t*>(base + size_t(j) * (3 * D) + 2 * D) + dp);
-    o0 = fmaf(p[j], bf16_lo(vv), o0);
-    o1 = fmaf(p[j], bf16_hi(vv), o1);
-  }
-  __syncthreads();
-  float* acc = p;                         // reuse: [8][64]
-  __syncthreads();
-  acc[slice * 64 + 2 * dp] = o0;
-  acc[slice * 64 + 2 * dp + 1] = o1;
-  __syncthreads();
-  if (threadIdx.x < 64) {
-    float o = 0.f;
+  const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;
+  float q[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(base) + sub), q);
 #pragma unroll
-    for (int s8 = 0; s8 < kThreads / 32; ++s8) o += acc[s8 * 64 + threadIdx.x];
-    out[row0 * D + h * 64 + threadIdx.x] = __float2bfloat16_rn(o / l);
+  for (int i = 0; i < 8; ++i) q[i] *= scale * LOG2E;                 // scores in the log2 domain
+  if (threadIdx.x < 64) osum[threadIdx.x] = 0.f;
+  float mx = -INFINITY;
+  const int n_pass = (N + kThreads / 8 - 1) / (kThreads / 8);   // warp-uniform trip count: the dot products shuffle
+  for (int it = 0; it < n_pass; ++it) {
+    const int j = grp + it * (kThreads / 8);
+    const bool ok = j < N;
+    float k[8];
+    unpack8(ok ? __ldg(reinterpret_cast<const uint4*>(base + size_t(j) * (3 * D) + D) + sub) : make_uint4(0u, 0u, 0u, 0u), k);
+    const float s = dot8_group(q, k);
+    if (ok) {
+      if (sub == 0) p[j] = s;
+      mx = fmaxf(mx, s);
+    }
   }
+  mx = block_reduce(mx, red, true);                                  // (its barriers also publish p[])
+  float sum = 0.f, o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = 0.f;
+  for (int j = grp; j < N; j += kThreads / 8) {                 // (no shuffles in this loop)
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(base + size_t(j) * (3 * D) + 2 * D) + sub), v);
+    const float e = exp2f(p[j] - mx);
+    if (sub == 0) sum += e;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaf(e, v[i], o[i]);
+  }
+  const float l = block_reduce(sum, red, false);
+  // the 32 key groups that share a piece: reduce over the 4 groups of a warp by shuffles, then shared atomics
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float t = o[i];
+    t += __shfl_xor_sync(0xffffffffu, t, 8);
+    t += __shfl_xor_sync(0xffffffffu, t, 16);
+    if ((threadIdx.x & 31) < 8) atomicAdd(&osum[8 * sub + i], t);
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) out[row0 * D + h * 64 + threadIdx.x] = __float2bfloat16_rn(osum[threadIdx.x] / l);
   if (threadIdx.x == 0) lse[row0 * H + h] = (mx + log2f(l)) * (1.0f / LOG2E);
 }
 
@@ -106,73 +112,65 @@ __global__ void __launch_bounds__(kThreads)
 attn_cls_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
                     const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
                     __nv_bfloat16* __restrict__ dqkv, int N, int H, float scale) {
-  __shared__ float q[64], dO[64], dq[64], red[kThreads / 32];
+  __shared__ float dqs[64], red[kThreads / 32];
   const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   const int D = H * 64;
   const size_t row0 = size_t(b) * N;
   const __nv_bfloat16* base = qkv + row0 * (3 * D) + h * 64;
-  float dl = 0.f;
-  if (threadIdx.x < 64) {
-    q[threadIdx.x] = __bfloat162float(base[threadIdx.x]);
-    const float g = __bfloat162float(dout[row0 * D + h * 64 + threadIdx.x]);
-    dO[threadIdx.x] = g;
-    dq[threadIdx.x] = 0.f;
-    dl = g * __bfloat162float(out[row0 * D + h * 64 + threadIdx.x]);
-  }
-  const float delta = block_reduce(dl, red, false);
-  const float l2 = lse[row0 * H + h] * LOG2E;
-  float dqa[64];
+  const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;
+  float q[8], g[8], oc[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(base) + sub), q);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(dout + row0 * D + h * 64) + sub), g);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(out + row0 * D + h * 64) + sub), oc);
+  const float delta = dot8_group(g, oc);                              // dO_cls . O_cls
+  const float l2 = __ldg(lse + row0 * H + h) * LOG2E;
+  if (threadIdx.x < 64) dqs[threadIdx.x] = 0.f;
+  __syncthreads();
+  float dq[8];
 #pragma unroll
-  for (int d = 0; d < 64; ++d) dqa[d] = 0.f;
-  for (int j = threadIdx.x; j < N; j += kThreads) {
-    const __nv_bfloat16* kr = base + size_t(j) * (3 * D) + D;
-    const float s = dot64(kr, q);
+  for (int i = 0; i < 8; ++i) dq[i] = 0.f;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  const int n_pass = (N + kThreads / 8 - 1) / (kThreads / 8);   // warp-uniform trip count: the dot products shuffle
+  for (int it = 0; it < n_pass; ++it) {
+    const int j = grp + it * (kThreads / 8);
+    const bool ok = j < N;
+    const __nv_bfloat16* kr = base + size_t(ok ? j : 0) * (3 * D) + D;
+    float k[8], v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(kr) + sub), k);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(kr + D) + sub), v);
+    const float s = dot8_group(q, k);
+    const float dp = dot8_group(g, v);
+    if (!ok) continue;
     const float pj = exp2f(s * (scale * LOG2E) - l2);
-    const float dp = dot64(kr + D, dO);
     const float ds = pj * (dp - delta) * scale;
     __nv_bfloat16* o = dqkv + (row0 + j) * (3 * D) + h * 64;
-    const uint4* k4 = reinterpret_cast<const uint4*>(kr);
-    uint4* dq4 = reinterpret_cast<uint4*>(o);
-    uint4* dk4 = reinterpret_cast<uint4*>(o + D);
-    uint4* dv4 = reinterpret_cast<uint4*>(o + 2 * D);
+    reinterpret_cast<uint4*>(o + D)[sub] = make_uint4(pack_bf16(ds * q[0], ds * q[1]), pack_bf16(ds * q[2], ds * q[3]),
+                                                      pack_bf16(ds * q[4], ds * q[5]), pack_bf16(ds * q[6], ds * q[7]));
+    reinterpret_cast<uint4*>(o + 2 * D)[sub] = make_uint4(pack_bf16(pj * g[0], pj * g[1]), pack_bf16(pj * g[2], pj * g[3]),
+                                                          pack_bf16(pj * g[4], pj * g[5]), pack_bf16(pj * g[6], pj * g[7]));
+    if (j > 0) reinterpret_cast<uint4*>(o)[sub] = zero;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const uint4 kk = __ldg(k4 + u);
-      const uint32_t kw[4] = {kk.x, kk.y, kk.z, kk.w};
-      uint32_t wk[4], wv[4];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int d = 8 * u + 2 * t;
-        dqa[d] = fmaf(ds, bf16_lo(kw[t]), dqa[d]);
-        dqa[d + 1] = fmaf(ds, bf16_hi(kw[t]), dqa[d + 1]);
-        wk[t] = pack_bf16(ds * q[d], ds * q[d + 1]);
-        wv[t] = pack_bf16(pj * dO[d], pj * dO[d + 1]);
-      }
-      dk4[u] = make_uint4(wk[0], wk[1], wk[2], wk[3]);
-      dv4[u] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-      if (j > 0) dq4[u] = make_uint4(0u, 0u, 0u, 0u);
-    }
+    for (int i = 0; i < 8; ++i) dq[i] = fmaf(ds, k[i], dq[i]);
   }
-  // dQ of the CLS row: warp-reduce every component, one shared atomic per warp and component
 #pragma unroll
-  for (int d = 0; d < 64; ++d) {
-    float v = dqa[d];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&dq[d], v);
+  for (int i = 0; i < 8; ++i) {
+    float t = dq[i];
+    t += __shfl_xor_sync(0xffffffffu, t, 8);
+    t += __shfl_xor_sync(0xffffffffu, t, 16);
+    if ((threadIdx.x & 31) < 8) atomicAdd(&dqs[8 * sub + i], t);
   }
   __syncthreads();
-  if (threadIdx.x < 64) dqkv[row0 * (3 * D) + h * 64 + threadIdx.x] = __float2bfloat16_rn(dq[threadIdx.x]);
+  if (threadIdx.x < 64) dqkv[row0 * (3 * D) + h * 64 + threadIdx.x] = __float2bfloat16_rn(dqs[threadIdx.x]);
+  (void)red;
 }
 
 }  // namespace
 
 int attn_cls_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t stream) {
   APLA_CHECK(B > 0 && N > 0 && H > 0 && N <= 8192, "attn_cls_fwd: bad shape B=%d N=%d H=%d", B, N, H);
-  const int pn = N < 512 ? 512 : N;
-  const size_t smem = (size_t(pn) + 64 + 8) * sizeof(float);
+  const size_t smem = (size_t(N) + 64 + 8) * sizeof(float);
   attn_cls_fwd_kernel<<<B * H, kThreads, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                                         reinterpret_cast<__nv_bfloat16*>(out), lse, N, pn, H, scale);
+                                                         reinterpret_cast<__nv_bfloat16*>(out), lse, N, H, scale);
   APLA_CUDA(cudaGetLastError());
   count_launch();
   return 0;

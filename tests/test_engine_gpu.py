@@ -101,17 +101,20 @@ def test_cls_only_last_block_is_exact():
             g = torch.Generator().manual_seed(4)
             images = torch.randn(6, 3, 224, 224, generator=g).cuda()
             labels = torch.randint(0, 37, (6,), generator=g).cuda()
-            for _ in range(2):
-                eng.step(images, labels)
+            eng.step(images, labels)
             torch.cuda.synchronize()
-            outs[(mode, r)] = (eng.logits.clone(), eng.loss.clone(), eng.grads.clone(), eng.params.clone())
+            first = eng.logits.clone()            # step 2 starts from parameters that carry the atomics' last-bit noise
+            eng.step(images, labels)
+            torch.cuda.synchronize()
+            outs[(mode, r)] = (first, eng.loss.clone(), eng.grads.clone(), eng.params.clone(), eng.logits.clone())
     for r in (16, 128):
         a, b, c = outs[(0, r)], outs[(1, r)], outs[(2, r)]
-        assert torch.equal(a[0], b[0])                                   # logits bit-identical
-        assert abs(float(a[1]) - float(b[1])) <= 1e-6 * abs(float(a[1]))
-        assert float((a[2] - b[2]).norm() / a[2].norm()) < 1e-5          # only the wgrad's fp32 atomics differ
+        assert torch.equal(a[0], b[0])                                   # first-step logits bit-identical
+        assert rel(b[4], a[4]) < 1e-4
+        assert abs(float(a[1]) - float(b[1])) <= 1e-5 * abs(float(a[1]))
+        assert float((a[2] - b[2]).norm() / a[2].norm()) < 1e-4          # only the wgrad's fp32 atomics differ
         assert float((a[3] - b[3]).norm() / a[3].norm()) < 1e-6
-        assert rel(c[0], a[0]) < 3e-3 and abs(float(c[1]) - float(a[1])) <= 2e-3 * abs(float(a[1]))
+        assert rel(c[4], a[4]) < 3e-3 and abs(float(c[1]) - float(a[1])) <= 2e-3 * abs(float(a[1]))
         assert rel(c[2], a[2]) < 6e-3 and cosine(c[2], a[2]) > 0.9999
 
 
