@@ -36,6 +36,10 @@ int apla_gemm_bias_ls_residual_fwd(const void* A, int lda, const void* W, int ld
                                    apla_stream_t stream) {
   return gemm_tn(EPI_RESID, A, W, M, N, K, lda, ldw, out, nullptr, bias, gamma, resid, ldo, S(stream), 0);
 }
+int apla_gemm_bias_ls_accumulate(const void* A, int lda, const void* W, int ldw, const float* bias, const float* gamma,
+                                 float* out, int ldo, int M, int N, int K, apla_stream_t stream) {
+  return gemm_tn(EPI_RED, A, W, M, N, K, lda, ldw, out, nullptr, bias, gamma, nullptr, ldo, S(stream), 0);
+}
 int apla_gemm_dgrad(const void* dY, int ldy, const void* Wt, int ldwt, void* dX, int ldx, int M, int K_in, int N_out,
                     apla_stream_t stream) {
   return gemm_tn(EPI_BIAS, dY, Wt, M, K_in, N_out, ldy, ldwt, dX, nullptr, nullptr, nullptr, nullptr, ldx, S(stream), 0);

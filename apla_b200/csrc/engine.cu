@@ -64,6 +64,10 @@ static const char* kGlobalNames[] = {
     "params", "grads", "exp_avg", "exp_avg_sq", "idx", "rowmap", "sumsq",
 };
 
+// optional global buffers (not checked by check_ready): "hyper" = float[3] {lr, 1 - beta1^t, sqrt(1 - beta2^t)} read by
+// the AdamW kernel instead of its launch arguments, so that a captured step can be replayed with new values
+static const char* kOptionalNames[] = {"hyper"};
+
 static int check_ready(Engine* e) {
   for (const char* n : kGlobalNames) {
     if (std::string(n) == "rowmap" && !e->full_rows) continue;
@@ -251,7 +255,7 @@ static int engine_optim(Engine* e, float gscale, float max_norm, float lr, float
   float* sumsq = e->get<float>("sumsq");
   if (int rc = grad_sumsq(grads, ar.n, gscale, sumsq, s)) return rc;
   if (int rc = adamw_step(params, grads, e->get<float>("exp_avg"), e->get<float>("exp_avg_sq"), ar.n, ar.n_decay, sumsq,
-                          gscale, max_norm, lr, wd, b1, b2, eps, step, s))
+                          gscale, max_norm, lr, wd, b1, b2, eps, step, s, e->get<float>("hyper")))
     return rc;
   // refresh the dense bf16 projection copies from the updated fp32 rows: one launch when the host laid the per-block
   // copies out back to back (apla_b200/engine.py does), one launch per block otherwise
@@ -306,6 +310,7 @@ int apla_engine_set_ptr(apla_engine_t h, const char* name, int block, void* p) {
   if (block < 0) {
     bool known = false;
     for (const char* k : kGlobalNames) known |= (n == k);
+    for (const char* k : kOptionalNames) known |= (n == k);
     APLA_CHECK(known, "apla_engine_set_ptr: unknown global buffer '%s'", name);
     e->g[n] = p;
     return 0;

@@ -167,7 +167,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue warps (both CTAs) =====================
-    constexpr bool kF32 = (EPI == EPI_RESID);
+    constexpr bool kF32 = (EPI == EPI_RESID || EPI == EPI_RED);
     constexpr bool kAux = (EPI == EPI_RESID || EPI == EPI_GELU_BWD || EPI == EPI_DELTA || EPI == EPI_MUL_F16);
     constexpr bool kBias = (EPI != EPI_GELU_BWD && EPI != EPI_DELTA && EPI != EPI_MUL_F16);
     constexpr bool kTwoOut = (EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_GELU_D);
@@ -334,6 +334,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
               }
               sts128(a, d[0], d[1], d[2], d[3]);
             }
+          } else if constexpr (EPI == EPI_RED) {
+            // out += gamma * (acc + bias): the residual never enters shared memory, the L2 adds (TMA reduce)
+            const float4* g4 = reinterpret_cast<const float4*>(gamma ? gamma + col : nullptr);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 g = gamma ? __ldg(g4 + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+              sts128(stg_addr(buf, lane, c), __float_as_uint(g.x * x[4 * c]), __float_as_uint(g.y * x[4 * c + 1]),
+                     __float_as_uint(g.z * x[4 * c + 2]), __float_as_uint(g.w * x[4 * c + 3]));
+            }
           } else if constexpr (EPI == EPI_RESID) {
             const float4* g4 = reinterpret_cast<const float4*>(gamma ? gamma + col : nullptr);
 #pragma unroll
@@ -386,6 +395,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                 const uint8_t* sb = staging + ew * 2 * kStgBuf + b * kStgBuf;
                 tma_store_2d(&tma_out, reinterpret_cast<const void*>(sb), col0, row0);
                 tma_store_2d(&tma_out2, reinterpret_cast<const void*>(sb + kStgBuf / 2), col0, row0);
+              } else if constexpr (EPI == EPI_RED) {
+                tma_reduce_add_2d(&tma_out, reinterpret_cast<const void*>(staging + ew * 2 * kStgBuf + b * kStgBuf), col0, row0);
               } else {
                 tma_store_2d(&tma_out, reinterpret_cast<const void*>(staging + ew * 2 * kStgBuf + b * kStgBuf), col0, row0);
               }
@@ -416,7 +427,7 @@ static int launch(const void* A, const void* B, int M, int N, int K, int lda, in
   CUtensorMap ta, tb, to, to2, tx;
   if (int rc = make_tmap_2d(&ta, A, 2, M, K, lda, BM, BK, true)) return rc;
   if (int rc = make_tmap_2d(&tb, B, 2, N, K, ldb, BN / 2, BK, true)) return rc;
-  constexpr int oelt = (EPI == EPI_RESID) ? 4 : 2;
+  constexpr int oelt = (EPI == EPI_RESID || EPI == EPI_RED) ? 4 : 2;
   if (EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_GELU_D) {
     if (int rc = make_tmap_2d_sw(&to, out, 2, M, N, ldo, 32, 32, 64)) return rc;
     if (int rc = make_tmap_2d_sw(&to2, out2, 2, M, N, ldo, 32, 32, 64)) return rc;
@@ -473,6 +484,8 @@ int gemm2_tn(int epi, const void* A, const void* B, int M, int N, int K, int lda
       return g2::dispatch<EPI_DELTA>(A, B, M, N, K, lda, ldb, out, out2, bias, gamma, aux, ldo, stream, bn);
     case EPI_BIAS_GELU_D:
       return g2::dispatch<EPI_BIAS_GELU_D>(A, B, M, N, K, lda, ldb, out, out2, bias, gamma, aux, ldo, stream, bn);
+    case EPI_RED:
+      return g2::dispatch<EPI_RED>(A, B, M, N, K, lda, ldb, out, out2, bias, gamma, aux, ldo, stream, bn);
     case EPI_MUL_F16:
       return g2::dispatch<EPI_MUL_F16>(A, B, M, N, K, lda, ldb, out, out2, bias, gamma, aux, ldo, stream, bn);
   }

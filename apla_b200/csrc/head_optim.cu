@@ -129,7 +129,12 @@ __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float scale
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, int64_t n, int64_t n_decay, const float* __restrict__ sumsq,
                              float gscale, float max_norm, float lr, float wd, float b1, float b2, float eps, float bc1,
-                             float bc2_sqrt) {
+                             float bc2_sqrt, const float* __restrict__ hyper) {
+  if (hyper) {   // {lr, 1 - beta1^t, sqrt(1 - beta2^t)} from device memory: the launch can be replayed from a CUDA graph
+    lr = hyper[0];
+    bc1 = hyper[1];
+    bc2_sqrt = hyper[2];
+  }
   float coef = gscale;
   if (max_norm > 0.f) {
     const float norm = sqrtf(*sumsq);
@@ -212,13 +217,13 @@ int grad_sumsq(const float* g, int64_t n, float scale, float* out, cudaStream_t 
 
 int adamw_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t n_decay, const float* sumsq,
                float gscale, float max_norm, float lr, float wd, float b1, float b2, float eps, int step,
-               cudaStream_t s) {
+               cudaStream_t s, const float* hyper) {
   APLA_CHECK(n > 0 && step >= 1, "adamw_step: empty arena or step < 1");
   const double bc1 = 1.0 - pow((double)b1, step);
   const double bc2 = 1.0 - pow((double)b2, step);
   const int grid = (int)((n + 1023) / 1024 < 1184 ? (n + 1023) / 1024 : 1184);
   adamw_kernel<<<grid, 256, 0, s>>>(p, g, m, v, n, n_decay, sumsq, gscale, max_norm, lr, wd, b1, b2, eps, (float)bc1,
-                                    (float)sqrt(bc2));
+                                    (float)sqrt(bc2), hyper);
   APLA_CUDA(cudaGetLastError());
   count_launch();
   return 0;

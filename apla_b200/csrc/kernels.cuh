@@ -6,7 +6,7 @@
 namespace apla {
 
 enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_RESID = 2, EPI_GELU_BWD = 3, EPI_F32_T = 4, EPI_DELTA = 5, EPI_BIAS_GELU_D = 6,
-       EPI_MUL_F16 = 7 };
+       EPI_MUL_F16 = 7, EPI_RED = 8 };
 
 // gemm.cu
 int gemm_tn(int epi, const void* A, const void* B, int M, int N, int K, int lda, int ldb, void* out, void* out2,
@@ -69,7 +69,7 @@ int head_bwd(const float* dlogits, const void* xn, const float* W, float* dW, fl
 int grad_sumsq(const float* g, int64_t n, float scale, float* out, cudaStream_t s);
 int adamw_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t n_decay, const float* sumsq,
                float gscale, float max_norm, float lr, float wd, float b1, float b2, float eps, int step,
-               cudaStream_t s);
+               cudaStream_t s, const float* hyper = nullptr);
 int proj_refresh(const float* w1, const float* b1, const int* idx, void* wfull, void* wfullT, float* bfull, int L,
                  int r, int D, int64_t w1_block_stride, int64_t b1_block_stride, cudaStream_t s);
 

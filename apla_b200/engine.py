@@ -49,7 +49,7 @@ def interpolate_pos_table(pos_embed: torch.Tensor, npatch: int) -> torch.Tensor:
 class FineTuneEngine:
     def __init__(self, model: nn.Module, batch_size: int, img_size: int, device="cuda", lr: float = 3e-5,
                  weight_decay: float = 1e-5, clip: float = 1.0, betas=(0.9, 0.999), adam_eps: float = 1e-8,
-                 process_group=None, cls_only_last_block: bool = True):
+                 process_group=None, cls_only_last_block: bool = True, use_graph: bool = True):
         require_device()
         # Only norm(x)[:, 0] of the last block reaches the head (vit.py:417-419): its projection, LayerNorm 2, MLP and
         # their input gradients run on the CLS rows only.  False = every token (identical results, for A/B checks).
@@ -60,6 +60,12 @@ class FineTuneEngine:
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if self._dist_on() else 1
         self.step_count = 0
+        # One CUDA graph per (images, labels) buffer pair replays the step's ~200 launches (single GPU only: with a
+        # process group the all-reduce runs on a side stream between two backward ranges).  lr and Adam's bias
+        # corrections reach the captured AdamW kernel through a 3-float device buffer refreshed before every replay.
+        self.use_graph = bool(use_graph) and self.world == 1
+        self._graphs: Dict[tuple, object] = {}
+        self._graph_seen: Dict[tuple, int] = {}
         self._keep: List[torch.Tensor] = []          # every device buffer the engine points at
         self._handle = None
         self._build(model, batch_size, img_size)
@@ -224,6 +230,9 @@ class FineTuneEngine:
             self._set("rowmap", self._dev(rowmap_all, torch.int32))
         else:
             self._set("dsub", self._new(T, r_pad))
+        self._hyper_dev = self._new(3, dtype=F32, zero=True)
+        if self.use_graph:
+            self._set("hyper", self._hyper_dev)
         self.images_dev = self._new(B, 3, img, img, dtype=F32)
         self.labels_dev = self._new(B, dtype=torch.int64)
         self._ar_stream = torch.cuda.Stream(device=self.device) if self.world > 1 else None
@@ -261,13 +270,17 @@ class FineTuneEngine:
                 sd[k].copy_(v.to(sd[k].device))
 
     # ------------------------------------------------------------------------------------------------------------
-    def forward(self, images: torch.Tensor, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """images fp32 [B,3,S,S] on the engine's device -> logits fp32 [B,C] (and loss/dlogits when labels given)."""
+    def _check_inputs(self, images, labels):
         B = self.shape["B"]
         if images.shape != self.images_dev.shape or images.dtype != F32 or not images.is_cuda:
             raise RuntimeError(f"images must be a CUDA fp32 tensor of shape {tuple(self.images_dev.shape)}")
         if labels is not None and (labels.dtype != torch.int64 or labels.shape != (B,) or not labels.is_cuda):
             raise RuntimeError("labels must be a CUDA int64 tensor of shape [B]")
+
+    def forward(self, images: torch.Tensor, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """images fp32 [B,3,S,S] on the engine's device -> logits fp32 [B,C] (and loss/dlogits when labels given)."""
+        B = self.shape["B"]
+        self._check_inputs(images, labels)
         images = images.contiguous()
         # CrossEntropyLoss(mean) over the local batch (wrappers.py:314); DDP later averages gradients over ranks
         LIB.call("apla_engine_forward", self._handle, ptr(images), ptr(labels), 1.0 / B, 1.0 / B, stream())
@@ -299,16 +312,60 @@ class FineTuneEngine:
             allreduce_arena(self.grads, lay, group=self.pg, which="late")
         cur.wait_stream(self._ar_stream)
 
+    def _push_hyper(self):
+        """lr and the bias corrections of the step about to run -> device (stream-ordered, before the AdamW kernel)."""
+        t = self.step_count
+        # a fresh PAGEABLE tensor: the runtime stages its bytes at call time, so the host may prepare the next step's
+        # values while this copy is still queued (a reused pinned buffer would be read when the copy executes)
+        self._hyper_dev.copy_(torch.tensor([self.lr, 1.0 - self.betas[0] ** t, (1.0 - self.betas[1] ** t) ** 0.5],
+                                           dtype=F32), non_blocking=True)
+
     def optim_step(self):
         self.step_count += 1
+        if self.use_graph:
+            self._push_hyper()
         LIB.call("apla_engine_optim", self._handle, 1.0 / self.world, float(self.clip or 0.0), self.lr, self.wd,
                  self.betas[0], self.betas[1], self.adam_eps, self.step_count, stream())
 
     def step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         """One Trainer.global_step on device-resident inputs; returns the (device) loss scalar."""
-        self.forward(images, labels)
-        self.backward()
-        self.optim_step()
+        if not self.use_graph:
+            self.forward(images, labels)
+            self.backward()
+            self.optim_step()
+            return self.loss
+        # graph path: a buffer pair is run eagerly the first time it is seen, captured on its second step (same launch
+        # sequence, nothing executes during capture) and replayed from then on
+        if not images.is_contiguous():
+            images = images.contiguous()      # (a fresh buffer every call: stays on the eager path)
+        key = (images.data_ptr(), labels.data_ptr(), tuple(images.shape))
+        g = self._graphs.get(key)
+        if g is None:
+            seen = self._graph_seen.get(key, 0)
+            self._graph_seen[key] = seen + 1
+            if seen == 0 or len(self._graphs) >= 4:
+                self.forward(images, labels)
+                self.backward()
+                self.optim_step()
+                return self.loss
+            self._check_inputs(images, labels)
+            if not images.is_contiguous():
+                raise RuntimeError("images must be contiguous")
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            count = self.step_count
+            with torch.cuda.graph(g):
+                LIB.call("apla_engine_forward", self._handle, ptr(images), ptr(labels), 1.0 / self.shape["B"],
+                         1.0 / self.shape["B"], stream())
+                LIB.call("apla_engine_backward", self._handle, self.shape["L"] - 1, 0, stream())
+                LIB.call("apla_engine_optim", self._handle, 1.0, float(self.clip or 0.0), self.lr, self.wd,
+                         self.betas[0], self.betas[1], self.adam_eps, 1, stream())
+            self.step_count = count
+            self._graphs[key] = g
+            self._graph_keep = getattr(self, "_graph_keep", []) + [(images, labels)]   # keep the buffers alive
+        self.step_count += 1
+        self._push_hyper()
+        g.replay()
         return self.loss
 
     def step_from_host(self, images_pinned: torch.Tensor, labels_pinned: torch.Tensor, lag: bool = True):

@@ -241,3 +241,13 @@ def attn_cls_bwd(qkv, out, dout, lse, H: int, scale: float, B: int, N: int, dqkv
         dqkv = torch.empty_like(qkv)
     LIB.call("apla_attn_cls_bwd", ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), B, N, H, scale, stream())
     return dqkv
+
+
+def gemm_bias_ls_accumulate(a, w, bias, gamma, out):
+    """out_f32 += gamma * (a @ w^T + bias), in place (TMA reduce-add epilogue)."""
+    require_device()
+    _chk(a, BF16, "a", 2); _chk(w, BF16, "w", 2); _chk(out, F32, "out", 2)
+    M, K = a.shape; N = w.shape[0]
+    LIB.call("apla_gemm_bias_ls_accumulate", ptr(a), _ld(a), ptr(w), _ld(w), ptr(bias), ptr(gamma), ptr(out), _ld(out),
+             M, N, K, stream())
+    return out

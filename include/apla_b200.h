@@ -44,6 +44,10 @@ int apla_gemm_bias_gelu_fwd(const void* A, int lda, const void* W, int ldw, cons
 int apla_gemm_bias_ls_residual_fwd(const void* A, int lda, const void* W, int ldw, const float* bias,
                                    const float* gamma, const float* resid, float* out, int ldo, int M, int N, int K,
                                    apla_stream_t stream);
+/* out_f32[M,N] += gamma_f32[N] * (A . W^T + bias): the same residual update performed IN PLACE -- the epilogue hands
+ * the scaled tile to the L2 as a TMA reduce-add, so the fp32 residual never passes through shared memory. */
+int apla_gemm_bias_ls_accumulate(const void* A, int lda, const void* W, int ldw, const float* bias, const float* gamma,
+                                 float* out, int ldo, int M, int N, int K, apla_stream_t stream);
 /* dX_bf16[M,K_in] = dY_bf16[M,N_out] . Wt_bf16[K_in,N_out]^T : input gradient of a frozen Linear; Wt is the
  * transposed weight ([in, out], prepared once because the weight is frozen).  No weight gradient is computed or
  * allocated (autograd prunes it the same way for requires_grad=False). */

@@ -118,6 +118,38 @@ def test_cls_only_last_block_is_exact():
         assert rel(c[2], a[2]) < 6e-3 and cosine(c[2], a[2]) > 0.9999
 
 
+def test_graph_replay_matches_eager():
+    """The step replayed from the engine's CUDA graph (default on one GPU; lr and Adam's bias corrections travel through a
+    device buffer) follows the eagerly launched step, and a learning-rate change reaches the captured AdamW kernel.
+    (Trajectories are compared at the reference lr: Adam's m / sqrt(v) amplifies the last-bit noise of the weight
+    gradient's fp32 atomics on near-zero entries, so two EAGER runs already differ by ~1e-5 after a few steps.)"""
+    from apla_b200.config import AplaConfig
+    from apla_b200.hostvit import VitArch, build_classifier
+    res = {}
+    for use_graph in (False, True):
+        model = build_classifier(VitArch(128, 2, 2), img_size=56, patch_size=14, n_classes=10, apla_config=AplaConfig(16), seed=0)
+        eng = _engine(model, 4, 56, use_graph=use_graph)
+        g = torch.Generator().manual_seed(4)
+        images = torch.randn(4, 3, 56, 56, generator=g).cuda()
+        labels = torch.randint(0, 10, (4,), generator=g).cuda()
+        losses = [float(eng.step(images, labels).item()) for _ in range(5)]
+        p5 = eng.params.clone()
+        eng.step(images, labels)
+        d_small = float((eng.params - p5).norm())
+        p6 = eng.params.clone()
+        eng.lr = 3e-3                                   # 100x: the update of the next step must grow ~100x
+        eng.step(images, labels)
+        d_big = float((eng.params - p6).norm())
+        torch.cuda.synchronize()
+        res[use_graph] = (losses, p5, d_big / d_small)
+        if use_graph:
+            assert len(eng._graphs) == 1
+    for a, b in zip(res[False][0], res[True][0]):
+        assert abs(a - b) <= 1e-4 * abs(a)
+    assert rel(res[True][1], res[False][1]) < 1e-5
+    assert 50 < res[True][2] < 150 and abs(res[True][2] - res[False][2]) < 0.1 * res[False][2]
+
+
 def test_sync_to_model_roundtrip():
     model, meta, arr = build_case("tiny_r16")
     m = meta["meta"]

@@ -86,6 +86,20 @@ def test_gemm_ls_residual_inplace():
     assert rel(r2, resid + (a.float() @ w.float().t() + bias)) < 1e-3
 
 
+def test_gemm_ls_accumulate_in_place():
+    ops = _cuda()
+    g = torch.Generator(device="cuda").manual_seed(21)
+    M, N, K = 1028, 768, 768
+    a = bf(torch.randn(M, K, device="cuda", generator=g))
+    w = bf(torch.randn(N, K, device="cuda", generator=g) * 0.02)
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    gamma = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    ref = resid + gamma * (a.float() @ w.float().t() + bias)
+    out = ops.gemm_bias_ls_accumulate(a, w, bias, gamma, resid.clone())
+    assert rel(out, ref) < 1e-3
+
+
 def test_gemm_dgrad_and_gelu_bwd():
     ops = _cuda()
     g = torch.Generator(device="cuda").manual_seed(3)

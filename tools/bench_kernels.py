@@ -60,6 +60,11 @@ def main():
     wp = (torch.randn(D, D, device=dev) * 0.02).bfloat16()
     t = timeit(lambda: ops.gemm_bias_ls_residual(x, wp, None, None, resid, out=resid))
     res.append(("gemm_ls_residual proj", t, 2 * T * D * D / t / 1e12, "TFLOP/s"))
+    gam = torch.ones(D, device=dev); bb = torch.zeros(D, device=dev)
+    t = timeit(lambda: ops.gemm_bias_ls_accumulate(x4, w2, bb, gam, resid))
+    res.append(("gemm_ls_accumulate fc2 (TMA reduce-add)", t, 2 * T * 4 * D * D / t / 1e12, "TFLOP/s"))
+    t = timeit(lambda: ops.gemm_bias_ls_accumulate(x, wp, bb, gam, resid))
+    res.append(("gemm_ls_accumulate proj (TMA reduce-add)", t, 2 * T * D * D / t / 1e12, "TFLOP/s"))
     w2t = w2.t().contiguous()
     dh = torch.empty(T, 4 * D, device=dev, dtype=torch.bfloat16)
     t = timeit(lambda: ops.gemm_dgrad_gelu_bwd(x, w2t, h, out=dh))
