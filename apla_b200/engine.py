@@ -20,6 +20,8 @@ from __future__ import annotations
 import math
 from typing import Dict, List, Optional
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -63,7 +65,10 @@ class FineTuneEngine:
         # One CUDA graph per (images, labels) buffer pair replays the step's ~200 launches (single GPU only: with a
         # process group the all-reduce runs on a side stream between two backward ranges).  lr and Adam's bias
         # corrections reach the captured AdamW kernel through a 3-float device buffer refreshed before every replay.
-        self.use_graph = bool(use_graph) and self.world == 1
+        # With a process group the step is three graphs (forward + upper backward | lower backward | optimiser) with the
+        # two gradient all-reduces launched eagerly between them on the side stream: capturing the NCCL collectives
+        # themselves hung on this stack (torch 2.11 / NCCL 2.28), and they are two launches anyway.
+        self.use_graph = bool(use_graph)
         self._graphs: Dict[tuple, object] = {}
         self._graph_seen: Dict[tuple, int] = {}
         self._keep: List[torch.Tensor] = []          # every device buffer the engine points at
@@ -352,20 +357,61 @@ class FineTuneEngine:
             if not images.is_contiguous():
                 raise RuntimeError("images must be contiguous")
             torch.cuda.current_stream().synchronize()
-            g = torch.cuda.CUDAGraph()
-            count = self.step_count
-            with torch.cuda.graph(g):
-                LIB.call("apla_engine_forward", self._handle, ptr(images), ptr(labels), 1.0 / self.shape["B"],
-                         1.0 / self.shape["B"], stream())
-                LIB.call("apla_engine_backward", self._handle, self.shape["L"] - 1, 0, stream())
-                LIB.call("apla_engine_optim", self._handle, 1.0, float(self.clip or 0.0), self.lr, self.wd,
+            L = self.shape["L"]
+            inv_b = 1.0 / self.shape["B"]
+
+            def capture(fn):
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, capture_error_mode="thread_local"):
+                    fn()
+                return gr
+
+            def optim():
+                LIB.call("apla_engine_optim", self._handle, 1.0 / self.world, float(self.clip or 0.0), self.lr, self.wd,
                          self.betas[0], self.betas[1], self.adam_eps, 1, stream())
-            self.step_count = count
+
+            if self.world == 1:
+                def whole():
+                    LIB.call("apla_engine_forward", self._handle, ptr(images), ptr(labels), inv_b, inv_b, stream())
+                    LIB.call("apla_engine_backward", self._handle, L - 1, 0, stream())
+                    optim()
+                g = (capture(whole),)
+            else:
+                from .dp import ArenaLayout
+                half = ArenaLayout(L=L, r=self.shape["r"], D=self.shape["D"], C=self.shape["C"]).split_block()
+
+                def upper():
+                    LIB.call("apla_engine_forward", self._handle, ptr(images), ptr(labels), inv_b, inv_b, stream())
+                    LIB.call("apla_engine_backward", self._handle, L - 1, half, stream())
+
+                def lower():
+                    LIB.call("apla_engine_backward", self._handle, half - 1, 0, stream())
+                g = (capture(upper), capture(lower) if half > 0 else None, capture(optim))
             self._graphs[key] = g
             self._graph_keep = getattr(self, "_graph_keep", []) + [(images, labels)]   # keep the buffers alive
         self.step_count += 1
         self._push_hyper()
-        g.replay()
+        if self.world == 1:
+            g[0].replay()
+            return self.loss
+        from .dp import ArenaLayout, allreduce_arena
+        lay = ArenaLayout(L=self.shape["L"], r=self.shape["r"], D=self.shape["D"], C=self.shape["C"])
+        cur = torch.cuda.current_stream()
+        g[0].replay()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        with torch.cuda.stream(self._ar_stream):
+            self._ar_stream.wait_event(ev)
+            allreduce_arena(self.grads, lay, group=self.pg, which="early")
+        if g[1] is not None:
+            g[1].replay()
+        ev2 = torch.cuda.Event()
+        ev2.record(cur)
+        with torch.cuda.stream(self._ar_stream):
+            self._ar_stream.wait_event(ev2)
+            allreduce_arena(self.grads, lay, group=self.pg, which="late")
+        cur.wait_stream(self._ar_stream)
+        g[2].replay()
         return self.loss
 
     def step_from_host(self, images_pinned: torch.Tensor, labels_pinned: torch.Tensor, lag: bool = True):
