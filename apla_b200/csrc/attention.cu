@@ -5,228 +5,18 @@
 // one code path.  Layout: qkv is [T, 3*H*64] with the (3, H, 64) split of appla_attn.py:53 along the last
 // dimension, out is [T, H*64] (heads merged, what the projection consumes), lse / delta are [T, H].
 //
-// Tensor-core path: warp-level mma.sync m16n8k16 with register-resident P / dS (flash-attention-2 style).
-// Round-1 implementation; the tcgen05/TMEM version of this kernel is the next step for this file.
+// This file is the dispatcher: sequences of up to 272 tokens (ViT at 224 px: 257 / 197 / 50) go to the persistent,
+// sequence-resident tcgen05 kernels (attention_fwd_sr.cu, attention_fused.cu), longer ones (1370 tokens at 518 px) to
+// the streaming tcgen05 kernels (attention_tc.cu, attention_tc_bwd.cu).  The first-generation mma.sync kernels and
+// the two-kernel sequence-resident backward that preceded the fused one were removed once the tcgen05 paths covered
+// every shape the tests exercise.
 #include "common.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
 
-#include <stdlib.h>
-
 namespace apla {
 
 namespace {
-
-constexpr int HD = 64;       // head dim
-constexpr int TS = 64;       // tile size (rows) for q and kv tiles
-constexpr int TILE_BYTES = TS * HD * 2;
-constexpr float LOG2E = 1.4426950408889634f;
-
-__device__ __forceinline__ uint32_t tile_addr(uint32_t base, int row, int chunk) {
-  return base + row * 128 + ((chunk ^ (row & 7)) << 4);
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
-  const int sz = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-// 64x64 bf16 tile, rows [row0, row0+64) of a matrix with leading dimension ld, rows >= nrows zero-filled
-__device__ __forceinline__ void load_tile(uint32_t sbase, const __nv_bfloat16* g, int ld, int row0, int nrows, int tid) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int idx = tid + i * 128;
-    const int r = idx >> 3, c = idx & 7;
-    const bool ok = (row0 + r) < nrows;
-    const __nv_bfloat16* src = g + size_t(ok ? row0 + r : 0) * ld + c * 8;
-    cp_async16(tile_addr(sbase, r, c), src, ok);
-  }
-}
-
-// A fragments (16 rows x 64 k) of the tile rows [r0, r0+16): f[kk][0..3]
-__device__ __forceinline__ void load_a_frags(uint32_t sbase, int r0, int lane, uint32_t (&f)[4][4]) {
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk)
-    ldsm_x4(tile_addr(sbase, r0 + (lane & 7) + ((lane >> 3) & 1) * 8, kk * 2 + (lane >> 4)), f[kk][0], f[kk][1],
-            f[kk][2], f[kk][3]);
-}
-
-// acc[16 x 64] (+)= A[16 x 64(k)] * Bt, with Bt given row-major as [n=64][k=64] in smem (non-transposed ldmatrix)
-__device__ __forceinline__ void mma_a_bT(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t sb, int lane) {
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-    for (int jp = 0; jp < 4; ++jp) {
-      uint32_t b0, b1, b2, b3;
-      ldsm_x4(tile_addr(sb, jp * 16 + (lane >> 4) * 8 + (lane & 7), kk * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
-      mma16816(acc[2 * jp], a[kk], b0, b1);
-      mma16816(acc[2 * jp + 1], a[kk], b2, b3);
-    }
-  }
-}
-// acc[16 x 64(n)] += P[16 x 64(k)] * B with B row-major [k=64][n=64] in smem (transposed ldmatrix);
-// P is given as fp32 accumulator-layout values p[8][4] and converted to bf16 A fragments on the fly.
-__device__ __forceinline__ void mma_p_b(float (&acc)[8][4], const float (&p)[8][4], uint32_t sb, int lane) {
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    uint32_t a[4];
-    a[0] = pack_bf16(p[2 * kk][0], p[2 * kk][1]);
-    a[1] = pack_bf16(p[2 * kk][2], p[2 * kk][3]);
-    a[2] = pack_bf16(p[2 * kk + 1][0], p[2 * kk + 1][1]);
-    a[3] = pack_bf16(p[2 * kk + 1][2], p[2 * kk + 1][3]);
-#pragma unroll
-    for (int jp = 0; jp < 4; ++jp) {
-      uint32_t b0, b1, b2, b3;
-      ldsm_x4_t(tile_addr(sb, kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), jp * 2 + (lane >> 4)), b0, b1, b2, b3);
-      mma16816(acc[2 * jp], a, b0, b1);
-      mma16816(acc[2 * jp + 1], a, b2, b3);
-    }
-  }
-}
-
-struct SeqInfo {
-  int row_start;
-  int n;
-};
-__device__ __forceinline__ SeqInfo seq_info(const int* cu, int b, int n_fixed) {
-  SeqInfo s;
-  if (cu) {
-    s.row_start = cu[b];
-    s.n = cu[b + 1] - s.row_start;
-  } else {
-    s.row_start = b * n_fixed;
-    s.n = n_fixed;
-  }
-  return s;
-}
-
-// ------------------------------------------------------------------------------------------------
-// forward
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
-                const int* __restrict__ cu_seqlens, int n_fixed, int H, float scale) {
-  __shared__ __align__(1024) uint8_t smem[5 * TILE_BYTES];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.y / H, h = blockIdx.y % H;
-  const SeqInfo sq = seq_info(cu_seqlens, b, n_fixed);
-  const int q0 = blockIdx.x * TS;
-  if (q0 >= sq.n) return;
-  const int D = H * HD, ld = 3 * D;
-  const __nv_bfloat16* Q = qkv + size_t(sq.row_start) * ld + h * HD;
-  const __nv_bfloat16* K = Q + D;
-  const __nv_bfloat16* V = Q + 2 * D;
-  const uint32_t sQ = smem_u32(smem), sK = sQ + TILE_BYTES, sV = sK + 2 * TILE_BYTES;
-  const float sl2 = scale * LOG2E;
-
-  load_tile(sQ, Q, ld, q0, sq.n, tid);
-  load_tile(sK, K, ld, 0, sq.n, tid);
-  load_tile(sV, V, ld, 0, sq.n, tid);
-  cp_async_commit();
-
-  const int nkv = (sq.n + TS - 1) / TS;
-  uint32_t qf[4][4];
-  float o[8][4];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-  const bool warp_active = (q0 + warp * 16) < sq.n;   // warps whose 16 rows are all padding only help loading
-
-  for (int t = 0; t < nkv; ++t) {
-    const int buf = t & 1;
-    if (t + 1 < nkv) {
-      load_tile(sK + (buf ^ 1) * TILE_BYTES, K, ld, (t + 1) * TS, sq.n, tid);
-      load_tile(sV + (buf ^ 1) * TILE_BYTES, V, ld, (t + 1) * TS, sq.n, tid);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    if (t == 0) load_a_frags(sQ, warp * 16, lane, qf);
-    if (warp_active) {
-      float s[8][4];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-      mma_a_bT(s, qf, sK + buf * TILE_BYTES, lane);
-      const int kv0 = t * TS;
-      if (kv0 + TS > sq.n) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = kv0 + 8 * j + 2 * (lane & 3);
-          if (c >= sq.n) s[j][0] = s[j][2] = -INFINITY;
-          if (c + 1 >= sq.n) s[j][1] = s[j][3] = -INFINITY;
-        }
-      }
-      float mx0 = m0, mx1 = m1;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
-        mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
-      }
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      const float c0 = exp2f((m0 - mx0) * sl2), c1 = exp2f((m1 - mx1) * sl2);
-      m0 = mx0; m1 = mx1;
-      const float ms0 = mx0 * sl2, ms1 = mx1 * sl2;
-      float rs0 = 0.f, rs1 = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s[j][0] = exp2f(s[j][0] * sl2 - ms0);
-        s[j][1] = exp2f(s[j][1] * sl2 - ms0);
-        s[j][2] = exp2f(s[j][2] * sl2 - ms1);
-        s[j][3] = exp2f(s[j][3] * sl2 - ms1);
-        rs0 += s[j][0] + s[j][1];
-        rs1 += s[j][2] + s[j][3];
-      }
-      l0 = l0 * c0 + rs0;
-      l1 = l1 * c1 + rs1;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1;
-      }
-      mma_p_b(o, s, sV + buf * TILE_BYTES, lane);
-    }
-    __syncthreads();
-  }
-  if (!warp_active) return;
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
-  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
-  __nv_bfloat16* O = out + size_t(sq.row_start) * D + h * HD;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = 8 * j + 2 * (lane & 3);
-    if (r0 < sq.n) *reinterpret_cast<uint32_t*>(O + size_t(r0) * D + c) = pack_bf16(o[j][0] * inv0, o[j][1] * inv0);
-    if (r1 < sq.n) *reinterpret_cast<uint32_t*>(O + size_t(r1) * D + c) = pack_bf16(o[j][2] * inv1, o[j][3] * inv1);
-  }
-  if ((lane & 3) == 0) {
-    if (r0 < sq.n) lse[size_t(sq.row_start + r0) * H + h] = m0 * scale + logf(l0);
-    if (r1 < sq.n) lse[size_t(sq.row_start + r1) * H + h] = m1 * scale + logf(l1);
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // backward: delta = rowsum(dO * O) per (token, head)
@@ -249,228 +39,15 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dout, const 
   if ((threadIdx.x & 7) == 0 && i < n_chunks) delta[i >> 3] = acc;
 }
 
-// ------------------------------------------------------------------------------------------------
-// backward: dK, dV.  One CTA per (kv tile, sequence, head); each warp owns 16 kv rows and keeps
-// S^T / dP^T (kv x q) in registers so P^T and dS^T feed the dV / dK MMAs without a shared-memory trip.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-attn_bwd_dkdv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
-                     const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
-                     const int* __restrict__ cu_seqlens, int n_fixed, int H, float scale) {
-  __shared__ __align__(1024) uint8_t smem[4 * TILE_BYTES + 2 * 2 * TS * 4];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.y / H, h = blockIdx.y % H;
-  const SeqInfo sq = seq_info(cu_seqlens, b, n_fixed);
-  const int kv0 = blockIdx.x * TS;
-  if (kv0 >= sq.n) return;
-  const int D = H * HD, ld = 3 * D;
-  const __nv_bfloat16* Q = qkv + size_t(sq.row_start) * ld + h * HD;
-  const __nv_bfloat16* K = Q + D;
-  const __nv_bfloat16* V = Q + 2 * D;
-  const __nv_bfloat16* dO = dout + size_t(sq.row_start) * D + h * HD;
-  const float* L = lse + size_t(sq.row_start) * H + h;
-  const float* Dl = delta + size_t(sq.row_start) * H + h;
-  const uint32_t sQ = smem_u32(smem), sdO = sQ + 2 * TILE_BYTES;
-  float* sL = reinterpret_cast<float*>(smem + 4 * TILE_BYTES);   // [2][64] lse*log2e
-  float* sD = sL + 2 * TS;                                       // [2][64] delta
-  const float sl2 = scale * LOG2E;
-
-  // stage K and V through the (still unused) q / dO buffers to build the A fragments
-  load_tile(sQ, K, ld, kv0, sq.n, tid);
-  load_tile(sdO, V, ld, kv0, sq.n, tid);
-  cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();
-  uint32_t kf[4][4], vf[4][4];
-  load_a_frags(sQ, warp * 16, lane, kf);
-  load_a_frags(sdO, warp * 16, lane, vf);
-  __syncthreads();
-
-  const int nq = (sq.n + TS - 1) / TS;
-  auto load_q_tile = [&](int t, int buf) {
-    load_tile(sQ + buf * TILE_BYTES, Q, ld, t * TS, sq.n, tid);
-    load_tile(sdO + buf * TILE_BYTES, dO, D, t * TS, sq.n, tid);
-    if (tid < TS) {
-      const int r = t * TS + tid;
-      sL[buf * TS + tid] = r < sq.n ? L[size_t(r) * H] * LOG2E : INFINITY;
-      sD[buf * TS + tid] = r < sq.n ? Dl[size_t(r) * H] : 0.f;
-    }
-  };
-  load_q_tile(0, 0);
-  cp_async_commit();
-
-  float dk[8][4], dv[8][4];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f;
-    dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f;
-  }
-  const bool warp_active = (kv0 + warp * 16) < sq.n;
-
-  for (int t = 0; t < nq; ++t) {
-    const int buf = t & 1;
-    if (t + 1 < nq) {
-      load_q_tile(t + 1, buf ^ 1);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    if (warp_active) {
-      const uint32_t q_s = sQ + buf * TILE_BYTES, do_s = sdO + buf * TILE_BYTES;
-      float p[8][4];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) p[j][0] = p[j][1] = p[j][2] = p[j][3] = 0.f;
-      mma_a_bT(p, kf, q_s, lane);                       // S^T = K Q^T   [kv x q]
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float2 l2 = *reinterpret_cast<const float2*>(sL + buf * TS + 8 * j + 2 * (lane & 3));
-        p[j][0] = exp2f(p[j][0] * sl2 - l2.x);
-        p[j][1] = exp2f(p[j][1] * sl2 - l2.y);
-        p[j][2] = exp2f(p[j][2] * sl2 - l2.x);
-        p[j][3] = exp2f(p[j][3] * sl2 - l2.y);
-      }
-      mma_p_b(dv, p, do_s, lane);                        // dV += P^T dO
-      float dp[8][4];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
-      mma_a_bT(dp, vf, do_s, lane);                      // dP^T = V dO^T [kv x q]
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float2 d2 = *reinterpret_cast<const float2*>(sD + buf * TS + 8 * j + 2 * (lane & 3));
-        dp[j][0] = p[j][0] * (dp[j][0] - d2.x);
-        dp[j][1] = p[j][1] * (dp[j][1] - d2.y);
-        dp[j][2] = p[j][2] * (dp[j][2] - d2.x);
-        dp[j][3] = p[j][3] * (dp[j][3] - d2.y);
-      }
-      mma_p_b(dk, dp, q_s, lane);                        // dK += dS^T Q
-    }
-    __syncthreads();
-  }
-  if (!warp_active) return;
-  const int r0 = kv0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
-  __nv_bfloat16* dK = dqkv + size_t(sq.row_start) * ld + D + h * HD;
-  __nv_bfloat16* dV = dK + D;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = 8 * j + 2 * (lane & 3);
-    if (r0 < sq.n) {
-      *reinterpret_cast<uint32_t*>(dK + size_t(r0) * ld + c) = pack_bf16(dk[j][0] * scale, dk[j][1] * scale);
-      *reinterpret_cast<uint32_t*>(dV + size_t(r0) * ld + c) = pack_bf16(dv[j][0], dv[j][1]);
-    }
-    if (r1 < sq.n) {
-      *reinterpret_cast<uint32_t*>(dK + size_t(r1) * ld + c) = pack_bf16(dk[j][2] * scale, dk[j][3] * scale);
-      *reinterpret_cast<uint32_t*>(dV + size_t(r1) * ld + c) = pack_bf16(dv[j][2], dv[j][3]);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// backward: dQ.  One CTA per (q tile, sequence, head), loop over kv tiles.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
-                   const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
-                   const int* __restrict__ cu_seqlens, int n_fixed, int H, float scale) {
-  __shared__ __align__(1024) uint8_t smem[4 * TILE_BYTES];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.y / H, h = blockIdx.y % H;
-  const SeqInfo sq = seq_info(cu_seqlens, b, n_fixed);
-  const int q0 = blockIdx.x * TS;
-  if (q0 >= sq.n) return;
-  const int D = H * HD, ld = 3 * D;
-  const __nv_bfloat16* Q = qkv + size_t(sq.row_start) * ld + h * HD;
-  const __nv_bfloat16* K = Q + D;
-  const __nv_bfloat16* V = Q + 2 * D;
-  const __nv_bfloat16* dO = dout + size_t(sq.row_start) * D + h * HD;
-  const uint32_t sK = smem_u32(smem), sV = sK + 2 * TILE_BYTES;
-  const float sl2 = scale * LOG2E;
-
-  load_tile(sK, Q, ld, q0, sq.n, tid);
-  load_tile(sV, dO, D, q0, sq.n, tid);
-  cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();
-  uint32_t qf[4][4], dof[4][4];
-  load_a_frags(sK, warp * 16, lane, qf);
-  load_a_frags(sV, warp * 16, lane, dof);
-  __syncthreads();
-
-  const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
-  const float lse0 = r0 < sq.n ? lse[size_t(sq.row_start + r0) * H + h] * LOG2E : INFINITY;
-  const float lse1 = r1 < sq.n ? lse[size_t(sq.row_start + r1) * H + h] * LOG2E : INFINITY;
-  const float dl0 = r0 < sq.n ? delta[size_t(sq.row_start + r0) * H + h] : 0.f;
-  const float dl1 = r1 < sq.n ? delta[size_t(sq.row_start + r1) * H + h] : 0.f;
-
-  load_tile(sK, K, ld, 0, sq.n, tid);
-  load_tile(sV, V, ld, 0, sq.n, tid);
-  cp_async_commit();
-  float dq[8][4];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
-  const bool warp_active = (q0 + warp * 16) < sq.n;
-  const int nkv = (sq.n + TS - 1) / TS;
-  for (int t = 0; t < nkv; ++t) {
-    const int buf = t & 1;
-    if (t + 1 < nkv) {
-      load_tile(sK + (buf ^ 1) * TILE_BYTES, K, ld, (t + 1) * TS, sq.n, tid);
-      load_tile(sV + (buf ^ 1) * TILE_BYTES, V, ld, (t + 1) * TS, sq.n, tid);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    if (warp_active) {
-      const uint32_t k_s = sK + buf * TILE_BYTES, v_s = sV + buf * TILE_BYTES;
-      float p[8][4], dp[8][4];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        p[j][0] = p[j][1] = p[j][2] = p[j][3] = 0.f;
-        dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
-      }
-      mma_a_bT(p, qf, k_s, lane);      // S = Q K^T
-      mma_a_bT(dp, dof, v_s, lane);    // dP = dO V^T
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        // padded kv columns hold K = V = 0, so their dS multiplies a zero K row: no masking needed
-        dp[j][0] = exp2f(p[j][0] * sl2 - lse0) * (dp[j][0] - dl0);
-        dp[j][1] = exp2f(p[j][1] * sl2 - lse0) * (dp[j][1] - dl0);
-        dp[j][2] = exp2f(p[j][2] * sl2 - lse1) * (dp[j][2] - dl1);
-        dp[j][3] = exp2f(p[j][3] * sl2 - lse1) * (dp[j][3] - dl1);
-      }
-      mma_p_b(dq, dp, k_s, lane);      // dQ += dS K
-    }
-    __syncthreads();
-  }
-  if (!warp_active) return;
-  __nv_bfloat16* dQ = dqkv + size_t(sq.row_start) * ld + h * HD;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = 8 * j + 2 * (lane & 3);
-    if (r0 < sq.n) *reinterpret_cast<uint32_t*>(dQ + size_t(r0) * ld + c) = pack_bf16(dq[j][0] * scale, dq[j][1] * scale);
-    if (r1 < sq.n) *reinterpret_cast<uint32_t*>(dQ + size_t(r1) * ld + c) = pack_bf16(dq[j][2] * scale, dq[j][3] * scale);
-  }
-}
-
 }  // namespace
 
 int attn_fwd(const void* qkv, void* out, float* lse, const int* cu_seqlens, int num_seqs, int max_seqlen,
              int total_tokens, int H,
              float scale, cudaStream_t stream) {
   APLA_CHECK(num_seqs > 0 && max_seqlen > 0 && H > 0, "attn_fwd: empty problem");
-  // default: tcgen05/TMEM kernel (attention_tc.cu); APLA_ATTN_IMPL=0 selects the mma.sync kernel below (A/B checks)
-  static const int impl = [] { const char* e = getenv("APLA_ATTN_IMPL"); return e ? atoi(e) : 3; }();
-  if (impl >= 3 && attn_fused_supported(max_seqlen))
+  if (attn_fused_supported(max_seqlen))
     return attn_fwd_sr(qkv, out, lse, cu_seqlens, num_seqs, max_seqlen, total_tokens, H, scale, stream);
-  if (impl != 0) return attn_fwd_tc(qkv, out, lse, cu_seqlens, num_seqs, max_seqlen, total_tokens, H, scale, stream);
-  dim3 grid(cdiv(max_seqlen, TS), num_seqs * H);
-  attn_fwd_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                            reinterpret_cast<__nv_bfloat16*>(out), lse, cu_seqlens, max_seqlen, H, scale);
-  APLA_CUDA(cudaGetLastError());
-  count_launch();
-  return 0;
+  return attn_fwd_tc(qkv, out, lse, cu_seqlens, num_seqs, max_seqlen, total_tokens, H, scale, stream);
 }
 
 int attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
@@ -485,28 +62,9 @@ int attn_bwd(const void* qkv, const void* out, const void* dout, const float* ls
     APLA_CUDA(cudaGetLastError());
     count_launch();
   }
-  // default (2): sequence-resident pipelined tcgen05 kernels for short sequences (attention_sr.cu), streaming
-  // tcgen05 kernels (attention_tc_bwd.cu) otherwise; APLA_ATTN_IMPL=1 forces the streaming kernels, 0 mma.sync
-  static const int impl = [] { const char* e = getenv("APLA_ATTN_IMPL"); return e ? atoi(e) : 3; }();
-  if (impl >= 3 && attn_fused_supported(max_seqlen))
+  if (attn_fused_supported(max_seqlen))
     return attn_bwd_fused(qkv, dout, lse, delta, dqkv, cu_seqlens, num_seqs, max_seqlen, total_tokens, H, scale, stream);
-  if (impl >= 2 && attn_sr_supported(max_seqlen))
-    return attn_bwd_sr(qkv, dout, lse, delta, dqkv, cu_seqlens, num_seqs, max_seqlen, total_tokens, H, scale, stream);
-  if (impl != 0)
-    return attn_bwd_tc(qkv, dout, lse, delta, dqkv, cu_seqlens, num_seqs, max_seqlen, total_tokens, H, scale, stream);
-  dim3 grid(cdiv(max_seqlen, TS), num_seqs * H);
-  attn_bwd_dkdv_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                                 reinterpret_cast<const __nv_bfloat16*>(dout), lse, delta,
-                                                 reinterpret_cast<__nv_bfloat16*>(dqkv), cu_seqlens, max_seqlen, H,
-                                                 scale);
-  APLA_CUDA(cudaGetLastError());
-  count_launch();
-  attn_bwd_dq_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                               reinterpret_cast<const __nv_bfloat16*>(dout), lse, delta,
-                                               reinterpret_cast<__nv_bfloat16*>(dqkv), cu_seqlens, max_seqlen, H, scale);
-  APLA_CUDA(cudaGetLastError());
-  count_launch();
-  return 0;
+  return attn_bwd_tc(qkv, dout, lse, delta, dqkv, cu_seqlens, num_seqs, max_seqlen, total_tokens, H, scale, stream);
 }
 
 }  // namespace apla

@@ -16,18 +16,13 @@ int gemm2_tn(int epi, const void* A, const void* B, int M, int N, int K, int lda
 int gemm_wgrad_nt(const void* A, const void* B, int M, int N, int K, int lda, int ldb, float* dW, int ldw,
                   const int* rowmap, int n_valid, cudaStream_t stream);
 
-// attention.cu
+// attention.cu (dispatch), attention_tc.cu / attention_tc_bwd.cu (streaming tcgen05 kernels, any sequence length)
 int attn_fwd(const void* qkv, void* out, float* lse, const int* cu_seqlens, int num_seqs, int max_seqlen,
              int total_tokens, int H,
              float scale, cudaStream_t stream);
 int attn_fwd_tc(const void* qkv, void* out, float* lse, const int* cu_seqlens, int num_seqs, int max_seqlen,
                 int total_tokens, int H, float scale, cudaStream_t stream);
 int attn_bwd_tc(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
-                const int* cu_seqlens, int num_seqs, int max_seqlen, int total_tokens, int H, float scale,
-                cudaStream_t stream);
-// attention_sr.cu: whole-sequence-resident pipelined kernels (max_seqlen <= 272)
-bool attn_sr_supported(int max_seqlen);
-int attn_bwd_sr(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
                 const int* cu_seqlens, int num_seqs, int max_seqlen, int total_tokens, int H, float scale,
                 cudaStream_t stream);
 // attention_fwd_sr.cu: persistent sequence-resident forward, max_seqlen <= 272
