@@ -53,10 +53,10 @@ __device__ __forceinline__ float dot8_group(const float (&a)[8], const float (&b
 __global__ void __launch_bounds__(kThreads)
 attn_cls_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N,
                     int H, float scale) {
-  extern __shared__ float sm[];          // p[N] | o[64] | red[8]
+  extern __shared__ float sm[];          // p[N] | o[8 warps][64] | red[8]
   float* p = sm;
   float* osum = p + N;
-  float* red = osum + 64;
+  float* red = osum + (kThreads / 32) * 64;
   const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   const int D = H * 64;
   const size_t row0 = size_t(b) * N;
@@ -66,7 +66,6 @@ attn_cls_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   unpack8(__ldg(reinterpret_cast<const uint4*>(base) + sub), q);
 #pragma unroll
   for (int i = 0; i < 8; ++i) q[i] *= scale * LOG2E;                 // scores in the log2 domain
-  if (threadIdx.x < 64) osum[threadIdx.x] = 0.f;
   float mx = -INFINITY;
   const int n_pass = (N + kThreads / 8 - 1) / (kThreads / 8);   // warp-uniform trip count: the dot products shuffle
   for (int it = 0; it < n_pass; ++it) {
@@ -93,16 +92,22 @@ attn_cls_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
     for (int i = 0; i < 8; ++i) o[i] = fmaf(e, v[i], o[i]);
   }
   const float l = block_reduce(sum, red, false);
-  // the 32 key groups that share a piece: reduce over the 4 groups of a warp by shuffles, then shared atomics
+  // the 32 key groups that share a piece: the 4 groups of a warp by shuffles, the 8 warps in a fixed order (no atomics:
+  // this row feeds the whole backward pass, run-to-run rounding noise here would reach every gradient)
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     float t = o[i];
     t += __shfl_xor_sync(0xffffffffu, t, 8);
     t += __shfl_xor_sync(0xffffffffu, t, 16);
-    if ((threadIdx.x & 31) < 8) atomicAdd(&osum[8 * sub + i], t);
+    if ((threadIdx.x & 31) < 8) osum[(threadIdx.x >> 5) * 64 + 8 * sub + i] = t;
   }
   __syncthreads();
-  if (threadIdx.x < 64) out[row0 * D + h * 64 + threadIdx.x] = __float2bfloat16_rn(osum[threadIdx.x] / l);
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) t += osum[w * 64 + threadIdx.x];
+    out[row0 * D + h * 64 + threadIdx.x] = __float2bfloat16_rn(t / l);
+  }
   if (threadIdx.x == 0) lse[row0 * H + h] = (mx + log2f(l)) * (1.0f / LOG2E);
 }
 
@@ -112,7 +117,7 @@ __global__ void __launch_bounds__(kThreads)
 attn_cls_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
                     const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
                     __nv_bfloat16* __restrict__ dqkv, int N, int H, float scale) {
-  __shared__ float dqs[64], red[kThreads / 32];
+  __shared__ float dqs[kThreads / 32][64];
   const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   const int D = H * 64;
   const size_t row0 = size_t(b) * N;
@@ -124,8 +129,6 @@ attn_cls_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
   unpack8(__ldg(reinterpret_cast<const uint4*>(out + row0 * D + h * 64) + sub), oc);
   const float delta = dot8_group(g, oc);                              // dO_cls . O_cls
   const float l2 = __ldg(lse + row0 * H + h) * LOG2E;
-  if (threadIdx.x < 64) dqs[threadIdx.x] = 0.f;
-  __syncthreads();
   float dq[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) dq[i] = 0.f;
@@ -157,18 +160,22 @@ attn_cls_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
     float t = dq[i];
     t += __shfl_xor_sync(0xffffffffu, t, 8);
     t += __shfl_xor_sync(0xffffffffu, t, 16);
-    if ((threadIdx.x & 31) < 8) atomicAdd(&dqs[8 * sub + i], t);
+    if ((threadIdx.x & 31) < 8) dqs[threadIdx.x >> 5][8 * sub + i] = t;   // fixed-order sum below: deterministic
   }
   __syncthreads();
-  if (threadIdx.x < 64) dqkv[row0 * (3 * D) + h * 64 + threadIdx.x] = __float2bfloat16_rn(dqs[threadIdx.x]);
-  (void)red;
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) t += dqs[w][threadIdx.x];
+    dqkv[row0 * (3 * D) + h * 64 + threadIdx.x] = __float2bfloat16_rn(t);
+  }
 }
 
 }  // namespace
 
 int attn_cls_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t stream) {
   APLA_CHECK(B > 0 && N > 0 && H > 0 && N <= 8192, "attn_cls_fwd: bad shape B=%d N=%d H=%d", B, N, H);
-  const size_t smem = (size_t(N) + 64 + 8) * sizeof(float);
+  const size_t smem = (size_t(N) + (kThreads / 32) * 64 + 8) * sizeof(float);
   attn_cls_fwd_kernel<<<B * H, kThreads, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                          reinterpret_cast<__nv_bfloat16*>(out), lse, N, H, scale);
   APLA_CUDA(cudaGetLastError());
