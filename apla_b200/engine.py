@@ -317,6 +317,13 @@ class FineTuneEngine:
             allreduce_arena(self.grads, lay, group=self.pg, which="late")
         cur.wait_stream(self._ar_stream)
 
+    def reset_graphs(self):
+        """Drop the captured CUDA graphs (they bake weight_decay, clip, betas and adam_eps -- everything except lr and the
+        step count, which travel through the device-side hyper buffer); the next steps re-capture."""
+        self._graphs.clear()
+        self._graph_seen.clear()
+        self._graph_keep = []
+
     def _push_hyper(self):
         """lr and the bias corrections of the step about to run -> device (stream-ordered, before the AdamW kernel)."""
         t = self.step_count
