@@ -43,7 +43,7 @@ def test_step_matches_reference_golden(name):
         ours = torch.cat([grads[k].flatten()[::sub].cpu() for k in meta["trainable"]])
         ref = torch.cat([torch.as_tensor(arr[tag + "grad/" + k]).flatten() for k in meta["trainable"]])
         assert cosine(ours, ref) >= 0.999, cosine(ours, ref)
-        assert rel(ours, ref) <= 3e-2, rel(ours, ref)
+        assert rel(ours, ref) <= 1e-2, rel(ours, ref)          # north_star: relative error <= 1e-2 (C3 sits at 9.6e-3)
         for k in meta["trainable"]:
             gref = arr[tag + "grad/" + k]
             if float(np.linalg.norm(gref)) < 1e-3 * float(ref.norm()):
