@@ -23,6 +23,15 @@ sys.path.insert(0, ROOT)
 
 METRIC = "ViT-B/14 APLA fine-tune images/sec/GPU at 1/2/4/8 B200; % bf16 tensor roofline"
 WORKLOAD = dict(arch="vit_base", img=224, table_img=518, patch=14, n_classes=555, partial_size=8, batch_per_gpu=64)
+# --workload: the default is the configuration the metric is quoted on (BASELINE.json configs[1] = C2); the others are
+# the remaining single-box shapes of SURVEY.md App. A through the SAME engine (reported in DESIGN.md, not the bench line
+# the driver reads).  c5 / vitl end in the classifier head: the mmseg decoder and the DINOv2 SSL heads are out of scope.
+WORKLOADS = {
+    "c2": WORKLOAD,
+    "c3": dict(WORKLOAD, partial_size=768),
+    "c5": dict(WORKLOAD, img=518, partial_size=768, batch_per_gpu=2),
+    "vitl": dict(WORKLOAD, arch="vit_large", partial_size=128),
+}
 
 
 def load_peaks():
@@ -106,14 +115,14 @@ def synthetic_batch(batch, img, n_classes, seed=1234, rank=0):
 # ----------------------------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm (oracle port) on the host cores
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_reference_steps(steps, warmup, batch):
+def cpu_reference_steps(steps, warmup, batch, w=WORKLOAD):
     """Times oracle.fine_tune_step (fp32 restatement of the reference step) on `batch` images of the workload."""
     import torch
     from oracle import apla_oracle as O
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    w = WORKLOAD
-    cfg = O.VitCfg(**O.VIT_B14, n_classes=w["n_classes"], partial_size=w["partial_size"])
+    cfg = O.VitCfg(**(O.VIT_L14 if w["arch"] == "vit_large" else O.VIT_B14), n_classes=w["n_classes"],
+                   partial_size=w["partial_size"])
     sd = O.build_state(cfg, seed=0)
     images, labels = O.synthetic_batch(batch, w["img"], w["n_classes"])
     st = O.AdamWState()
@@ -125,7 +134,8 @@ def cpu_reference_steps(steps, warmup, batch):
     ts = ts[warmup:]
     sec = sum(ts) / len(ts)
     return dict(value=batch / sec, unit="images/s", cores=threads, kind="port",
-                sample=f"oracle/apla_oracle.py fine_tune_step, ViT-B/14 r=8 224px fp32, batch {batch}, "
+                sample=f"oracle/apla_oracle.py fine_tune_step, {w['arch']}/14 r={w['partial_size']} {w['img']}px fp32, "
+                       f"batch {batch}, "
                        f"{len(ts)} steps after {warmup} warm-up, {sec * 1e3:.0f} ms/step"), sec
 
 
@@ -134,12 +144,14 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 2))
-    cb, sec = cpu_reference_steps(steps, warmup, batch=8)
+    w = WORKLOADS[args.workload]
+    cb, sec = cpu_reference_steps(steps, warmup, batch=min(8, w["batch_per_gpu"]), w=w)
     line = dict(metric=METRIC, value=cb["value"], unit="images/s", n_gpus=args.gpus, steps=steps, warmup=warmup,
                 ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference",
-                config=dict(workload="ViT-B/14 dinov2-arch APLA partial_size=8 fine-tune step, 224px, 555 classes; CPU "
-                                     "sample: batch 8 per step", **WORKLOAD),
+                config=dict(workload=f"{w['arch']}/14 dinov2-arch APLA partial_size={w['partial_size']} fine-tune step, "
+                                     f"{w['img']}px, 555 classes; CPU sample: batch {min(8, w['batch_per_gpu'])} per step",
+                            **w),
                 cpu_baseline=cb,
                 e2e=dict(value=cb["value"], unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
@@ -231,7 +243,7 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if args.gpus != world:
         raise RuntimeError(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 through torch.distributed.run")
-    w = WORKLOAD
+    w = WORKLOADS[args.workload]
     B = args.batch or w["batch_per_gpu"]
 
     # identical weights and APLA indices on every rank: same seed, same constructor order
@@ -291,10 +303,13 @@ def run_gpu(args):
             metric=METRIC, value=B * world / (ms_step * 1e-3), unit="images/s", n_gpus=world, steps=args.steps,
             warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
             dtype="bf16", data="synthetic", per_gpu=B / (ms_step * 1e-3), loss=loss,
-            config=dict(workload="ViT-B/14 dinov2-arch (518-px pos table, LayerScale, qkv bias) APLA partial_size=8 "
-                                 "supervised fine-tune step, 224px, 555 classes, AdamW lr 3e-5 wd 1e-5 clip 1.0",
-                        global_batch=B * world, batch_per_gpu=B, tokens_per_image=257, parallelism=f"dp{world}",
-                        l2="per-step working set ~5 GB >> 126 MB L2 (activations of 12 blocks), no flush needed",
+            config=dict(workload=f"{'ViT-L' if w['arch'] == 'vit_large' else 'ViT-B'}/14 dinov2-arch (518-px pos table, "
+                                 f"LayerScale, qkv bias) APLA partial_size={w['partial_size']} supervised fine-tune step, "
+                                 f"{w['img']}px, 555 classes, AdamW lr 3e-5 wd 1e-5 clip 1.0",
+                        global_batch=B * world, batch_per_gpu=B, tokens_per_image=eng.shape["N"],
+                        parallelism=f"dp{world}",
+                        l2=f"per-step working set ~{sum(t.numel() * t.element_size() for t in eng._keep) / 1e9:.1f} GB "
+                           ">> 126 MB L2 (saved activations of every block), no flush needed",
                         **{k: v for k, v in w.items() if k != "batch_per_gpu"}),
             # dominant kernel (largest share of the step), algorithmic FLOPs 2*M*N*K per launch / live CUDA-event time;
             # peak = measured burst cuBLAS bf16 (kernel timed alone); `step` = the whole step against the sustained peak
@@ -302,7 +317,8 @@ def run_gpu(args):
                           unit="TFLOP/s", frac=dom["tflops"] / peaks["tflops_burst"],
                           peak_source=f"{peaks['source']} MEASURED_PEAKS.json bf16_tflops (burst)",
                           us_per_launch=dom["us_per_launch"], flops_per_launch=dom["flops_per_launch"],
-                          launches_timed=dom["launches"], traffic=DOMINANT_TRAFFIC_BYTES,
+                          launches_timed=dom["launches"],
+                          traffic=DOMINANT_TRAFFIC_BYTES if (args.workload in ("c2", "c3") and B == 64) else None,
                           traffic_note="dram read+write bytes per launch, ncu --set full (profiles/ncu_r1d_summary.md)",
                           fc1_gelu_kernel=dict(**fc1, frac=fc1["tflops"] / peaks["tflops_burst"]),
                           step=dict(scope="whole step (all kernels); EXECUTED algorithmic FLOPs: SURVEY.md App. B minus the "
@@ -318,7 +334,7 @@ def run_gpu(args):
                      h2d_bytes_per_step=images_pin.numel() * 4 + labels_pin.numel() * 8, d2h_bytes_per_step=4),
             gpu_launches=launches_per_step * args.steps, gpu_launches_per_step=launches_per_step, clocks=clocks)
         if world == 1 and not args.no_cpu:
-            cb, _ = cpu_reference_steps(steps=3, warmup=1, batch=8)
+            cb, _ = cpu_reference_steps(steps=3, warmup=1, batch=min(8, w["batch_per_gpu"]), w=w)
             line["cpu_baseline"] = cb
         print(json.dumps(line))
     if world > 1:
@@ -334,6 +350,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (default: the workload's 64)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS),
+                    help="c2 = BASELINE.json configs[1] (the metric's configuration, default); c3 / c5 / vitl: other shapes")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -93,9 +93,14 @@ def param_groups(model):
     return [{"params": reg}, {"params": noreg, "weight_decay": 0.0}]
 
 
+ONLY = set(sys.argv[1:])        # optional: names of the cases to (re)generate; default all
+
+
 def run_case(name, vit, apla_vit, *, ctor, apla_cfg, n_classes, batch, img, is_multi_gpu=False,
              perturb=True, sub=1, steps=1, full_grads=False):
     import contextlib, io
+    if ONLY and name not in ONLY:
+        return
     torch.manual_seed(0)
     with contextlib.redirect_stdout(io.StringIO()):
         model = RefClassifier(vit, apla_vit, None, _AttrDict(apla_cfg), n_classes, is_multi_gpu, ctor=ctor)
@@ -193,6 +198,19 @@ def main():
     run_case("c2_vitb14_inds128", vit, apla_vit, ctor=c2,
              apla_cfg={"partial_size": 128, "inds_path": dst}, n_classes=555,
              batch=2, img=224, is_multi_gpu=True, sub=127)
+
+    # C5 backbone shape: ViT-B/14 at 518 px = 1370 tokens, pos table used un-interpolated (vit.py:424-425), r = 768,
+    # 2 images per GPU (mmseg config); the segmentation decoder is a third-party framework, so the step ends in the
+    # same classifier head as C2 -- what is pinned here is the long-sequence block path
+    run_case("c5_vitb14_518_r768", vit, apla_vit, ctor=c2, apla_cfg={"partial_size": 768}, n_classes=555,
+             batch=2, img=518, sub=1543)
+
+    # C4 backbone shape: ViT-L/14 (D 1024, 16 heads, 24 blocks), r = 128, supervised head, batch 2
+    def vl(v):
+        return v.vit_large(pretrained=False, img_size=[518], patch_size=14, pretrained_type="dinov2",
+                           is_memory_efficient=True, block_conf=bc)
+    run_case("vitl14_r128", vit, apla_vit, ctor=vl, apla_cfg={"partial_size": 128}, n_classes=555,
+             batch=2, img=224, sub=509)
 
 
 if __name__ == "__main__":

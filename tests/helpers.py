@@ -21,6 +21,8 @@ CASES = {
     "c2_vitb14_r8": ("vit_base", 518, 14),
     "c3_vitb14_r768": ("vit_base", 518, 14),
     "c2_vitb14_inds128": ("vit_base", 518, 14),
+    "c5_vitb14_518_r768": ("vit_base", 518, 14),      # 1370 tokens: the streaming long-sequence attention kernels
+    "vitl14_r128": ("vit_large", 518, 14),            # C4's backbone shape (D 1024, 16 heads, 24 blocks)
 }
 
 

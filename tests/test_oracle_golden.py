@@ -23,6 +23,8 @@ CASES = {
     "c2_vitb14_r8": (O.VIT_B14, {}),
     "c3_vitb14_r768": (O.VIT_B14, {}),
     "c2_vitb14_inds128": (O.VIT_B14, {"inds_file": "inds-vit_b-rand_128.json"}),
+    "c5_vitb14_518_r768": (O.VIT_B14, {}),
+    "vitl14_r128": (O.VIT_L14, {}),
 }
 
 
