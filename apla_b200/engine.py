@@ -274,6 +274,89 @@ class FineTuneEngine:
             for k, v in self.named_params().items():
                 sd[k].copy_(v.to(sd[k].device))
 
+    # ---- checkpoint interchange with the reference (apla_b200/checkpoint.py) ---------------
+    def _named_shapes(self):
+        return [(k, self.shapes[k]) for k in self.trainable_names()]
+
+    def state_dict(self):
+        """The Classifier's CPU state dict with the engine's current trainable tensors written back
+        (what bases.py:455-458 saves under 'state_dict')."""
+        from .checkpoint import model_to_cpu_state
+        torch.cuda.current_stream().synchronize()
+        self.sync_to_model()
+        return model_to_cpu_state(self.model)
+
+    def optimizer_state_dict(self) -> dict:
+        """`torch.optim.AdamW.state_dict()` of the reference's optimiser (two groups of wrappers.py:205-221) holding
+        the engine's moments and step count."""
+        from .checkpoint import optimizer_state_dict
+        torch.cuda.current_stream().synchronize()
+        m = {k: self.exp_avg[self.slices[k]] for k in self.trainable_names()}
+        v = {k: self.exp_avg_sq[self.slices[k]] for k in self.trainable_names()}
+        return optimizer_state_dict(self._named_shapes(), m, v, self.step_count, lr=self.lr, betas=self.betas,
+                                    eps=self.adam_eps, weight_decay=self.wd)
+
+    def load_state_dict(self, sd):
+        """Take the TRAINABLE tensors of a reference state dict into the arena and refresh the dense projection copies.
+        Frozen tensors are laid out (bf16, both orientations) when the engine is built, so they are only checked: a
+        state dict whose APLA indices differ from the ones this engine was built with is refused."""
+        bb = self.model.backbone
+        for l, blk in enumerate(bb.blocks):
+            k = f"backbone.blocks.{l}.attn.inds"
+            if k in sd and hasattr(blk.attn, "inds") and not torch.equal(sd[k].cpu().long(), blk.attn.inds.cpu().long()):
+                raise RuntimeError(f"{k} differs from the indices this engine was built with; load the checkpoint into "
+                                   "the model (load_from_pretrained) before constructing the engine")
+        missing = [k for k in self.trainable_names() if k not in sd]
+        if missing:
+            raise KeyError(f"state dict lacks trainable tensors: {missing[:4]}{' ...' if len(missing) > 4 else ''}")
+        for k in self.trainable_names():
+            t = sd[k]
+            if tuple(t.shape) != tuple(self.shapes[k]):
+                raise RuntimeError(f"{k}: checkpoint shape {tuple(t.shape)}, engine {tuple(self.shapes[k])}")
+            self.params[self.slices[k]] = t.detach().to(self.device, F32).reshape(-1)
+        self._refresh_proj()
+        self.sync_to_model()
+
+    def _refresh_proj(self):
+        s = self.shape
+        o = self.offsets
+        LIB.call("apla_proj_refresh", self.params[o["w1"]:].data_ptr(), self.params[o["b1"]:].data_ptr(), ptr(self.idx),
+                 ptr(self._wproj_all), ptr(self._wprojT_all), ptr(self._bproj_all), s["L"], s["r"], s["D"],
+                 s["r"] * s["D"], s["r"], stream())
+
+    def load_optimizer_state_dict(self, opt_sd: dict):
+        """Adam moments, step count and hyper-parameters from a reference optimiser state dict (bases.py:423-428)."""
+        from .checkpoint import split_optimizer_state
+        m, v, step, hyper = split_optimizer_state(opt_sd, self._named_shapes())
+        for k in self.trainable_names():
+            self.exp_avg[self.slices[k]] = m[k].to(self.device).reshape(-1)
+            self.exp_avg_sq[self.slices[k]] = v[k].to(self.device).reshape(-1)
+        self.step_count = step
+        changed = (hyper["betas"] != tuple(self.betas) or hyper["eps"] != self.adam_eps
+                   or hyper["weight_decay"] != self.wd)
+        self.lr, self.betas, self.adam_eps, self.wd = hyper["lr"], hyper["betas"], hyper["eps"], hyper["weight_decay"]
+        if changed:
+            self.reset_graphs()         # captured graphs bake everything except lr and the step count
+
+    def save_session(self, path: str, *, iters: Optional[int] = None, epoch: int = 0, parameters=None,
+                     best_val_target=None, original_state=None) -> str:
+        """Write `<path>` in the reference's session format (bases.py:448-468)."""
+        from .checkpoint import save_session
+        return save_session(path, state_dict=self.state_dict(), optimizer=self.optimizer_state_dict(),
+                            iters=self.step_count if iters is None else iters, epoch=epoch, parameters=parameters,
+                            best_val_target=best_val_target, original_state=original_state)
+
+    def load_session(self, path: str, restore_only_model: bool = False) -> dict:
+        """bases.py:405-433: model tensors, then (unless restore_only_model) iters / epoch / optimiser state.
+        Returns the checkpoint dict (iters, epoch, parameters, ... for the caller's bookkeeping)."""
+        from .checkpoint import load_session_file
+        ckpt = load_session_file(path)
+        self.load_state_dict(ckpt["state_dict"])
+        if not restore_only_model:
+            self.load_optimizer_state_dict(ckpt["optimizer"])
+        torch.cuda.current_stream().synchronize()
+        return ckpt
+
     # ------------------------------------------------------------------------------------------------------------
     def _check_inputs(self, images, labels):
         B = self.shape["B"]

@@ -160,3 +160,69 @@ def test_sync_to_model_roundtrip():
     sd = dict(model.named_parameters())
     for k in meta["trainable"]:
         assert rel(sd[k].detach().flatten(), arr["s0/param/" + k]) <= 1e-3
+
+
+def test_session_checkpoint_resume_and_reference_optimizer(tmp_path):
+    """a session file written by the engine (reference format, bases.py:448-468) resumes in a fresh
+    engine to the same parameters, and its optimiser state continues identically inside torch.optim.AdamW built over
+    the reference's parameter groups (wrappers.py:205-221)."""
+    from apla_b200 import checkpoint as C
+    model, meta, _ = build_case("tiny_r16")
+    m = meta["meta"]
+    eng = _engine(model, m["batch"], m["img"])
+    images, labels = synthetic_batch(m["batch"], m["img"], m["n_classes"])
+    images, labels = images.cuda(), labels.cuda()
+    for _ in range(2):
+        eng.forward(images, labels)
+        eng.backward()
+        eng.optim_step()
+    path = str(tmp_path / "apla_tiny.pth")
+    eng.save_session(path, epoch=1)
+    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    assert tuple(ckpt) == C.SESSION_KEYS and ckpt["iters"] == 2 and ckpt["epoch"] == 1
+    assert len(ckpt["optimizer"]["state"]) == len(meta["trainable"])
+
+    # (1) resume in a fresh engine over a freshly built model
+    model2, _, _ = build_case("tiny_r16")
+    eng2 = _engine(model2, m["batch"], m["img"])
+    got = eng2.load_session(path)
+    assert got["iters"] == 2 and eng2.step_count == 2
+    for k, v in eng.named_params().items():
+        assert torch.equal(v, eng2.named_params()[k]), k
+    for e in (eng, eng2):
+        e.forward(images, labels)
+        e.backward()
+    torch.cuda.synchronize()
+    assert torch.equal(eng.logits, eng2.logits)          # dense projection copies were refreshed from the loaded rows
+    grads = {k: v.detach().cpu().clone() for k, v in eng.named_grads().items()}
+    for e in (eng, eng2):
+        e.optim_step()
+    torch.cuda.synchronize()
+    for k, v in eng.named_params().items():
+        assert rel(eng2.named_params()[k], v) <= 1e-6, k
+
+    # (2) the same third step inside the reference's optimiser, started from the saved file
+    model3, _, _ = build_case("tiny_r16")
+    C.load_from_pretrained(model3, path)
+    reg, noreg = [], []
+    for name, p in model3.named_parameters():
+        if p.requires_grad:
+            (noreg if (name.endswith(".bias") or len(p.shape) == 1) else reg).append(p)
+    opt = torch.optim.AdamW([{"params": reg}, {"params": noreg, "weight_decay": 0.0}], lr=1.0)
+    opt.load_state_dict(ckpt["optimizer"])
+    named = dict(model3.named_parameters())
+    for k, g in grads.items():
+        named[k].grad = g.clone()
+    torch.nn.utils.clip_grad_norm_([p for p in model3.parameters() if p.requires_grad], 1.0)
+    opt.step()
+    for k, v in eng.named_params().items():
+        assert rel(v, named[k].detach()) <= 1e-6, (k, rel(v, named[k].detach()))
+        # the update itself, not just the (dominant) unchanged part of the weights
+        before = ckpt["state_dict"][k]
+        assert cosine(v.cpu() - before, named[k].detach() - before) >= 0.9999, k
+
+    # (3) a checkpoint with other APLA indices is refused
+    sd = {k: v.clone() for k, v in ckpt["state_dict"].items()}
+    sd["backbone.blocks.0.attn.inds"] = sd["backbone.blocks.0.attn.inds"].flip(0)
+    with pytest.raises(RuntimeError, match="indices"):
+        eng2.load_state_dict(sd)
