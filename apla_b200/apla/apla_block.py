@@ -1,0 +1,232 @@
+"""`FusedAplaBlock` / `fuse_apla_blocks`: the whole transformer block around an APLA attention as ONE autograd node.
+
+`APLA_Attention` (appla_attn.py) replaces the reference's attention module only; the block around it
+(`Block.forward` src/utils/transformers/vit.py:279-288: LayerNorm, LayerScale, residual adds, `Mlp` :162-168 with exact
+GELU; `NestedTensorBlock` src/self_supervised/dinov2/layers/block.py:244-288 for lists of crops) would still run as
+~10 ATen kernels per direction, keep every LayerNorm / fc1 / GELU output for autograd and compute nothing in bf16
+tensor-core GEMMs unless the caller wraps it in autocast.  `fuse_apla_blocks(model)` swaps each block whose attention
+is an `APLA_Attention` for a `FusedAplaBlock` that holds the SAME sub-modules under the SAME names (state-dict keys and
+checkpoints unchanged) and runs forward and backward through the kernels the step engine uses:
+
+  forward   LN1 -> qkv GEMM -> fused attention (saves log-sum-exp) -> proj GEMM (+bias, xLayerScale, +residual, fp32)
+            -> LN2 -> fc1 GEMM (+bias, GELU, saves gelu' in fp16) -> fc2 GEMM (+bias, xLayerScale, +residual, fp32)
+  backward  LayerScale+cast -> fc2 dgrad x gelu' -> fc1 dgrad -> LN2' (+residual grad, xLayerScale, APLA column gather)
+            -> weight gradient of the r trainable projection rows -> proj dgrad (+attention delta) -> attention'
+            -> qkv dgrad -> LN1' (+residual grad)
+
+Saved per block: the two fp32 residual checkpoints, qkv, the attention output, log-sum-exp and gelu' -- no LayerNorm
+output, no [B,H,N,N] probabilities, no fc1 pre- or post-activation.  Gradients flow to EVERY token of the input (dense
+prediction heads, SSL patch losses) and to `proj_weight1` / `proj_bias1`; nothing is computed for frozen tensors.
+Accepts `[B,N,D]` tensors (vit.py Block) and lists of `[b_i,N_i,D]` crops, which are packed and attended
+block-diagonally (dinov2 NestedTensorBlock.forward_nested; get_attn_bias_and_cat block.py:191-217).
+
+The residual stream is fp32 inside the node whatever the input dtype (what autocast keeps in fp32); the
+output has the input's dtype.  CUDA (sm_100a) only, no fallback; dropout / drop-path / stochastic depth must be off
+(all shipped reference configs run them at 0).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .._lib import require_device
+from .appla_attn import APLA_Attention, _pad64
+
+
+class _AplaBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, blk, cu_seqlens, seqlens):
+        at = blk.attn
+        ws = at._working_set(x.device)
+        ms = blk._mlp_working_set(x.device)
+        D = x.shape[-1]
+        x_in = x.reshape(-1, D).to(torch.float32).contiguous()
+        T = x_in.shape[0]
+        if cu_seqlens is None:
+            num_seqs, max_len = (x.shape[0], x.shape[1]) if x.dim() == 3 else (1, T)
+        else:
+            num_seqs, max_len = len(seqlens), max(seqlens)
+        eps1, eps2 = float(blk.norm1.eps), float(blk.norm2.eps)
+        h = ops.layernorm_fwd(x_in, ms["ln1w"], ms["ln1b"], eps1)
+        qkv = ops.gemm_bias(h, ws["wqkv"], ws["bqkv"])
+        ao, lse = ops.attn_fwd(qkv, at.num_heads, float(at.scale), num_seqs, max_len, cu_seqlens=cu_seqlens)
+        x_mid = ops.gemm_bias_ls_residual(ao, ws["wproj"], ws["bproj"], ms["g1"], x_in)
+        ops.layernorm_fwd(x_mid, ms["ln2w"], ms["ln2b"], eps2, out=h)
+        dgelu, g = ops.gemm_bias_gelu_dgelu(h, ms["wfc1"], ms["bfc1"])
+        x_out = ops.gemm_bias_ls_residual(g, ms["wfc2"], ms["bfc2"], ms["g2"], x_mid)
+        ctx.blk, ctx.ws, ctx.ms = blk, ws, ms
+        ctx.geom = (num_seqs, max_len, cu_seqlens)
+        ctx.x_dtype, ctx.x_shape = x.dtype, x.shape
+        ctx.save_for_backward(x_in, x_mid, qkv, ao, lse, dgelu)
+        return x_out.view(x.shape).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        blk, ws, ms = ctx.blk, ctx.ws, ctx.ms
+        at = blk.attn
+        x_in, x_mid, qkv, ao, lse, dgelu = ctx.saved_tensors
+        num_seqs, max_len, cu = ctx.geom
+        D = ctx.x_shape[-1]
+        r = at.partial_size
+        want_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dx_out = dy.reshape(-1, D).to(torch.float32).contiguous()
+        # MLP branch
+        dyb = ops.ls_cast(dx_out, ms["g2"])
+        dh = ops.gemm_dgrad_mul(dyb, ms["wfc2T"], dgelu)
+        dln = ops.gemm_dgrad(dh, ms["wfc1T"])
+        del dh
+        # dx_mid = dx_out + LN2'(dln); dyb = bf16(gamma1 * dx_mid) is the gradient at the projection output; its APLA
+        # columns are gathered in the same pass when only a few rows are trainable
+        sub = None
+        if want_w and ws["rowmap"] is None:
+            sub = torch.empty(dx_out.shape[0], _pad64(r), device=dy.device, dtype=torch.bfloat16)
+        dx_mid = ops.layernorm_bwd(dln, x_mid, ms["ln2w"], float(blk.norm2.eps), dres=dx_out, dxb=dyb, gamma=ms["g1"],
+                                   sub=sub, idx=ws["idx"] if sub is not None else None, r=r if sub is not None else 0)
+        dw1 = db1 = dx = None
+        if want_w:
+            dw1 = torch.zeros(r, D, device=dy.device, dtype=torch.float32)
+            db1 = torch.zeros(r, device=dy.device, dtype=torch.float32)
+            if sub is None:
+                ops.proj_wgrad(dyb, ao, dw1, r, rowmap=ws["rowmap"])
+                ops.colsum(dyb, db1, D, rowmap=ws["rowmap"])
+            else:
+                ops.proj_wgrad(sub, ao, dw1, r)
+                ops.colsum(sub, db1, r)
+        if ctx.needs_input_grad[0]:
+            d_ao, delta = ops.gemm_dgrad_delta(dyb, ws["wprojT"], ao)
+            dqkv = ops.attn_bwd(qkv, None, d_ao, lse, at.num_heads, float(at.scale), num_seqs, max_len, cu_seqlens=cu,
+                                delta=delta)
+            ops.gemm_dgrad(dqkv, ws["wqkvT"], out=dln)
+            dx = ops.layernorm_bwd(dln, x_in, ms["ln1w"], float(blk.norm1.eps), dres=dx_mid, dx=dx_mid)
+            dx = dx.view(ctx.x_shape).to(ctx.x_dtype)
+        return dx, dw1, db1, None, None, None
+
+
+def _gamma_of(ls) -> Optional[torch.Tensor]:
+    """LayerScale's per-channel vector (vit.py:236-244; dinov2/layers/layer_scale.py:15-27), None for nn.Identity."""
+    if ls is None or isinstance(ls, nn.Identity):
+        return None
+    g = getattr(ls, "gamma", None)
+    if g is None:
+        raise TypeError(f"cannot fuse a block whose ls module is {type(ls).__name__} (expected LayerScale or Identity)")
+    return g
+
+
+def _drop_rate(mod) -> float:
+    if mod is None or isinstance(mod, nn.Identity):
+        return 0.0
+    return float(getattr(mod, "drop_prob", None) or getattr(mod, "p", 0.0) or 0.0)
+
+
+class FusedAplaBlock(nn.Module):
+    """Holds the wrapped block's sub-modules under their own names; only `forward` is replaced."""
+
+    def __init__(self, block: nn.Module):
+        super().__init__()
+        if not isinstance(block.attn, APLA_Attention):
+            raise TypeError("FusedAplaBlock needs a block whose .attn is an apla_b200 APLA_Attention "
+                            "(run build_apla / replace_attn_with_apla first)")
+        fc1, fc2 = block.mlp.fc1, block.mlp.fc2
+        act = getattr(block.mlp, "act", None)
+        if act is not None and not (isinstance(act, nn.GELU) and getattr(act, "approximate", "none") == "none"):
+            raise TypeError("the fused MLP implements exact (erf) GELU only (vit.py:153)")
+        if fc1.in_features % 64 or fc1.out_features % 64 or fc2.out_features != fc1.in_features:
+            raise ValueError("fused block needs embed and hidden sizes that are multiples of 64")
+        for name, child in block.named_children():       # norm1, attn, ls1, drop_path*, norm2, mlp, ls2 -- same keys
+            self.add_module(name, child)
+        for opt in ("ls1", "ls2"):
+            if not hasattr(self, opt):
+                self.add_module(opt, nn.Identity())
+        self.sample_drop_ratio = float(getattr(block, "sample_drop_ratio", 0.0) or 0.0)
+        self._ms = None
+        self._ms_key = None
+
+    # ---- bf16 working copies of the frozen MLP / norm / LayerScale tensors -----------------------------------------
+    def _mlp_working_set(self, device):
+        tk = APLA_Attention._tkey
+        g1, g2 = _gamma_of(self.ls1), _gamma_of(self.ls2)
+        srcs = [self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias, self.norm1.weight,
+                self.norm1.bias, self.norm2.weight, self.norm2.bias, g1, g2]
+        key = tuple(None if t is None else tk(t) for t in srcs)
+        if self._ms is None or self._ms_key != key:
+            bf, f32 = torch.bfloat16, torch.float32
+
+            def dev(t, dt):
+                return None if t is None else t.detach().to(device=device, dtype=dt).contiguous()
+
+            with torch.no_grad():
+                w1, w2 = dev(self.mlp.fc1.weight, bf), dev(self.mlp.fc2.weight, bf)
+                zeros = lambda n: torch.zeros(n, device=device, dtype=f32)          # noqa: E731
+                self._ms = dict(
+                    wfc1=w1, wfc1T=w1.t().contiguous(), wfc2=w2, wfc2T=w2.t().contiguous(),
+                    bfc1=dev(self.mlp.fc1.bias, f32) if self.mlp.fc1.bias is not None else zeros(w1.shape[0]),
+                    bfc2=dev(self.mlp.fc2.bias, f32) if self.mlp.fc2.bias is not None else zeros(w2.shape[0]),
+                    ln1w=dev(self.norm1.weight, f32), ln1b=dev(self.norm1.bias, f32),
+                    ln2w=dev(self.norm2.weight, f32), ln2b=dev(self.norm2.bias, f32), g1=dev(g1, f32), g2=dev(g2, f32))
+            self._ms_key = key
+        return self._ms
+
+    def _check(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("apla_b200.FusedAplaBlock runs on CUDA (sm_100a) only; there is no CPU fallback")
+        require_device()
+        if self.training:
+            at = self.attn
+            rates = [at.attn_drop.p, at.proj_drop.p, _drop_rate(getattr(self.mlp, "drop", None)), self.sample_drop_ratio]
+            rates += [_drop_rate(getattr(self, n, None)) for n in ("drop_path", "drop_path1", "drop_path2")]
+            if any(p > 0 for p in rates):
+                raise RuntimeError("fused APLA block supports dropout / drop-path rate 0 only "
+                                   "(all shipped reference configs use 0)")
+        for p in (self.norm1.weight, self.norm2.weight, self.mlp.fc1.weight, self.mlp.fc2.weight):
+            if p.requires_grad:
+                raise RuntimeError("fused APLA block computes weight gradients for proj_weight1 / proj_bias1 only; "
+                                   "norm / MLP parameters must be frozen (build_apla's freeze policy)")
+
+    def _run_fused(self, x, cu=None, seqlens=None):
+        at = self.attn
+        return _AplaBlockFn.apply(x, at.proj_weight1, at.proj_bias1, self, cu, seqlens)
+
+    def forward(self, x_or_x_list, return_attention: bool = False, return_intermediate: bool = False):
+        """`[B,N,D]` -> `[B,N,D]` (vit.py:279-288) or list of `[b_i,N_i,D]` -> list (dinov2 block.py:274-288)."""
+        if return_attention or return_intermediate:
+            raise RuntimeError("the fused block never materialises the [B,H,N,N] attention probabilities "
+                               "(vit.py:282-287 visualisation paths): un-fuse the model for them")
+        if isinstance(x_or_x_list, torch.Tensor):
+            self._check(x_or_x_list)
+            return self._run_fused(x_or_x_list)
+        xs: Sequence[torch.Tensor] = list(x_or_x_list)
+        if not xs:
+            raise AssertionError("empty crop list")
+        self._check(xs[0])
+        D = xs[0].shape[-1]
+        seqlens: List[int] = []
+        for t in xs:
+            seqlens += [t.shape[1]] * t.shape[0]
+        packed = torch.cat([t.reshape(1, -1, D) for t in xs], dim=1)                     # [1, sum b_i*N_i, D]
+        cu = torch.zeros(len(seqlens) + 1, dtype=torch.int32)
+        cu[1:] = torch.tensor(seqlens, dtype=torch.int32).cumsum(0)
+        out = self._run_fused(packed, cu.to(packed.device), seqlens)
+        sizes = [t.shape[0] * t.shape[1] for t in xs]
+        return [o.reshape(t.shape) for o, t in zip(out.split(sizes, dim=1), xs)]
+
+
+def fuse_apla_blocks(model: nn.Module) -> nn.Module:
+    """Swap every block of `model.blocks` (a backbone, or a Classifier's `.backbone`) that carries an `APLA_Attention`
+    for a `FusedAplaBlock` in place.  Parameters, buffers and state-dict keys are untouched.  Returns `model`."""
+    bb = model if hasattr(model, "blocks") else getattr(model, "backbone", None)
+    if bb is None or not hasattr(bb, "blocks"):
+        raise AttributeError("model exposes no .blocks (SURVEY.md 8b: what the host model must expose)")
+    n = 0
+    for i, blk in enumerate(bb.blocks):
+        if isinstance(blk, FusedAplaBlock):
+            continue
+        if isinstance(getattr(blk, "attn", None), APLA_Attention):
+            bb.blocks[i] = FusedAplaBlock(blk)
+            n += 1
+    if n == 0 and not any(isinstance(b, FusedAplaBlock) for b in bb.blocks):
+        raise RuntimeError("no block carries an APLA_Attention: call build_apla(config, model, attn_class) first "
+                           "(multi-GPU partial_size='full' keeps the stock attention and cannot be fused)")
+    return model

@@ -85,6 +85,11 @@ int apla_gather_cols(const void* dy, int64_t ld, void* sub, int64_t ld_sub, cons
   return gather_cols(dy, ld, sub, ld_sub, idx, r, r_pad, rows, S(stream));
 }
 
+int apla_ls_cast(const float* x, int64_t ldx, const float* gamma, void* out, int64_t ldo, int rows, int D,
+                 apla_stream_t stream) {
+  return ls_cast(x, ldx, gamma, out, ldo, rows, D, S(stream));
+}
+
 int apla_attn_fwd(const void* qkv, void* out, float* lse, const int32_t* cu_seqlens, int num_seqs, int max_seqlen,
                   int total_tokens,
                   int H, float scale, apla_stream_t stream) {

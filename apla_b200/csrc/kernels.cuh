@@ -50,6 +50,8 @@ int layernorm_bwd(const void* dy, int64_t ld_dy, const float* x, int64_t ldx, co
                   int64_t ld_sub, const int* idx, int r, int r_pad, int rows, int D, float eps, cudaStream_t stream);
 int gather_cols(const void* dy, int64_t ld, void* sub, int64_t ld_sub, const int* idx, int r, int r_pad, int rows,
                 cudaStream_t stream);
+int ls_cast(const float* x, int64_t ldx, const float* gamma, void* out, int64_t ldo, int rows, int D,
+            cudaStream_t stream);
 int colsum(const void* a, int64_t ld, int rows, int n, float* out, const int* rowmap, cudaStream_t stream);
 int patchify(const float* img, void* out, int B, int S, int p, int kpad, cudaStream_t stream);
 int assemble_tokens(const void* patch, const float* cls, const float* pos, float* x, int B, int P, int D,

@@ -155,6 +155,25 @@ __global__ void gather_cols_kernel(const __nv_bfloat16* __restrict__ dy, int64_t
   sub[row * ld_sub + j] = j < r ? dy[row * ld + __ldg(idx + j)] : __float2bfloat16_rn(0.f);
 }
 
+// out_bf16[t, d] = gamma[d] * x_f32[t, d] (gamma NULL = 1): LayerScale backward + down-cast of a residual gradient that
+// arrives from outside the fused chain (autograd handing the block-level Function its dY); 4 elements per thread
+__global__ void ls_cast_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
+                               __nv_bfloat16* __restrict__ out, int64_t ldo, int rows, int D4) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= int64_t(rows) * D4) return;
+  const int row = int(i / D4), c = int(i % D4) * 4;
+  float4 v = *reinterpret_cast<const float4*>(x + row * ldx + c);
+  if (gamma) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+  }
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&lo);
+  pk.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(out + row * ldo + c) = pk;
+}
+
 // column sums of a bf16 [rows, n] matrix -> fp32 out[map(j)] (+=): bias gradient of the trainable rows
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ a, int64_t ld, int rows, int n, float* __restrict__ out,
                               const int* __restrict__ rowmap, int rows_per_block) {
@@ -286,6 +305,17 @@ int gather_cols(const void* dy, int64_t ld, void* sub, int64_t ld_sub, const int
   APLA_CHECK(total > 0, "gather_cols: empty");
   gather_cols_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), ld, reinterpret_cast<__nv_bfloat16*>(sub), ld_sub, idx, r, r_pad, rows);
+  APLA_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int ls_cast(const float* x, int64_t ldx, const float* gamma, void* out, int64_t ldo, int rows, int D,
+            cudaStream_t stream) {
+  APLA_CHECK(rows > 0 && D > 0 && D % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0, "ls_cast: bad shape rows=%d D=%d", rows, D);
+  const int64_t total = int64_t(rows) * (D / 4);
+  ls_cast_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, ldx, gamma, reinterpret_cast<__nv_bfloat16*>(out),
+                                                                      ldo, rows, D / 4);
   APLA_CUDA(cudaGetLastError());
   count_launch();
   return 0;

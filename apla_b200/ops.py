@@ -175,6 +175,17 @@ def layernorm_bwd(dy, x, w, eps: float, dres=None, dx=None, dxb=None, gamma=None
     return dx
 
 
+def ls_cast(x, gamma=None, out=None):
+    """out_bf16 = gamma * x_f32 (gamma None = plain down-cast)."""
+    require_device()
+    _chk(x, F32, "x", 2)
+    rows, D = x.shape
+    if out is None:
+        out = torch.empty(rows, D, device=x.device, dtype=BF16)
+    LIB.call("apla_ls_cast", ptr(x), _ld(x), ptr(gamma), ptr(out), _ld(out), rows, D, stream())
+    return out
+
+
 def gather_cols(dy, idx, r: int, r_pad: int, out=None):
     require_device()
     _chk(dy, BF16, "dy", 2)

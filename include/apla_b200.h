@@ -94,6 +94,11 @@ int apla_layernorm_bwd(const void* dy, int64_t ld_dy, const float* x, int64_t ld
 int apla_gather_cols(const void* dy, int64_t ld, void* sub, int64_t ld_sub, const int32_t* idx, int r, int r_pad,
                      int rows, apla_stream_t stream);
 
+/* out_bf16 = gamma * x_f32 (gamma NULL = 1): LayerScale backward (vit.py:243-244) + down-cast of a residual-stream
+ * gradient entering the fused block from autograd (Block.forward vit.py:279-288 seen from its output). */
+int apla_ls_cast(const float* x, int64_t ldx, const float* gamma, void* out, int64_t ldo, int rows, int D,
+                 apla_stream_t stream);
+
 /* --- attention ------------------------------------------------------------------------------------------ */
 /* out_bf16[T, H*64] = softmax(scale * q k^T) v per sequence and head; lse_f32[T, H] saved for backward.
  * qkv_bf16[T, 3*H*64] laid out (3, H, 64) along the last dim (appla_attn.py:53-54).  cu_seqlens = NULL: num_seqs

@@ -1,0 +1,157 @@
+"""Block-level drop-in on the B200 (`apla_b200.apla.fuse_apla_blocks` / `FusedAplaBlock`): the whole `Block.forward`
+(src/utils/transformers/vit.py:279-288) and the packed multi-crop `NestedTensorBlock.forward_nested`
+(src/self_supervised/dinov2/layers/block.py:274-288) as one autograd node, against
+ (a) the fp32 CPU oracle's `block_forward` on the same tensors (output, gradient w.r.t. EVERY input token, weight / bias
+     gradient of the trainable projection rows), dense and block-diagonal, and
+ (b) the golden vectors recorded from the unmodified reference for a whole model built from fused blocks.
+Bars (BASELINE.json north_star): relative error <= 1e-2, gradient cosine >= 0.999."""
+import pytest
+import torch
+
+from helpers import build_case, cosine, rel, synthetic_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def _oracle_block(model, l, x_cpu, seqlens=None):
+    """oracle.block_forward on block l of `model` (CPU fp32, autograd on x / proj_weight1 / proj_bias1)."""
+    from oracle import apla_oracle as O
+    sd = {k: (v.detach().float() if v.is_floating_point() else v.detach()).cpu().clone()
+          for k, v in model.state_dict().items()}
+    b = f"backbone.blocks.{l}."
+    w1 = sd[b + "attn.proj_weight1"].requires_grad_(True)
+    b1 = sd[b + "attn.proj_bias1"].requires_grad_(True)
+    xr = x_cpu.clone().requires_grad_(True)
+    blk = model.backbone.blocks[l]
+    out = O.block_forward(sd, b, xr, blk.attn.num_heads, float(blk.norm1.eps), seqlens)
+    return out, xr, w1, b1
+
+
+@pytest.mark.parametrize("name,l,B,N", [("tiny_r16", 1, 3, 257), ("c1_vits16_r32_pert", 5, 2, 197),
+                                        ("tiny_interp_r128", 0, 2, 50), ("c5_vitb14_518_r768", 3, 1, 1370)])
+def test_fused_block_matches_oracle_dense(name, l, B, N):
+    _need_gpu()
+    from apla_b200.apla import FusedAplaBlock, fuse_apla_blocks
+    model, _, _ = build_case(name)
+    D = model.backbone.embed_dim
+    g = torch.Generator().manual_seed(11)
+    x_cpu = torch.randn(B, N, D, generator=g)
+    dy_cpu = torch.randn(B, N, D, generator=g)
+    ref, xr, w1, b1 = _oracle_block(model, l, x_cpu)
+    ref.backward(dy_cpu)
+
+    keys = list(model.state_dict().keys())
+    fuse_apla_blocks(model.cuda())
+    assert list(model.state_dict().keys()) == keys                      # same checkpoint keys after the swap
+    blk = model.backbone.blocks[l]
+    assert isinstance(blk, FusedAplaBlock)
+    x = x_cpu.cuda().requires_grad_(True)
+    out = blk(x)
+    assert out.shape == x.shape and out.dtype == x.dtype
+    out.backward(dy_cpu.cuda())
+    torch.cuda.synchronize()
+    at = blk.attn
+    assert rel(out.detach(), ref.detach()) <= 1e-2, rel(out.detach(), ref.detach())
+    assert rel(x.grad, xr.grad) <= 1e-2 and cosine(x.grad, xr.grad) >= 0.999, rel(x.grad, xr.grad)
+    assert rel(at.proj_weight1.grad, w1.grad) <= 1e-2, rel(at.proj_weight1.grad, w1.grad)
+    assert cosine(at.proj_weight1.grad, w1.grad) >= 0.999
+    assert rel(at.proj_bias1.grad, b1.grad) <= 1e-2
+    # nothing else received a gradient
+    for n_, p in blk.named_parameters():
+        if "proj_weight1" not in n_ and "proj_bias1" not in n_:
+            assert p.grad is None, n_
+    # input that does not require grad (block 0 behind a frozen embedding): only the weight gradient is computed
+    for p in blk.parameters():
+        p.grad = None
+    blk(x_cpu.cuda()).backward(dy_cpu.cuda())
+    assert rel(at.proj_weight1.grad, w1.grad) <= 1e-2
+
+
+def test_fused_block_packed_crops():
+    """dinov2 multi-crop: a list of [b_i, N_i, D] crop tensors is packed and attended block-diagonally; every crop's
+    tokens get gradients (iBOT / dense losses), the projection rows get one summed weight gradient."""
+    _need_gpu()
+    from apla_b200.apla import fuse_apla_blocks
+    model, _, _ = build_case("tiny_r16")
+    D = model.backbone.embed_dim
+    g = torch.Generator().manual_seed(5)
+    crops = [torch.randn(2, 257, D, generator=g), torch.randn(4, 50, D, generator=g)]
+    dys = [torch.randn(c.shape, generator=g) for c in crops]
+    seqlens = [257, 257, 50, 50, 50, 50]
+    packed = torch.cat([c.reshape(1, -1, D) for c in crops], 1)
+    ref, xr, w1, b1 = _oracle_block(model, 1, packed, seqlens)
+    ref.backward(torch.cat([d.reshape(1, -1, D) for d in dys], 1))
+
+    fuse_apla_blocks(model.cuda())
+    blk = model.backbone.blocks[1]
+    xs = [c.cuda().requires_grad_(True) for c in crops]
+    outs = blk(xs)
+    assert isinstance(outs, list) and [o.shape for o in outs] == [c.shape for c in crops]
+    torch.autograd.backward(outs, [d.cuda() for d in dys])
+    torch.cuda.synchronize()
+    got = torch.cat([o.detach().reshape(1, -1, D) for o in outs], 1)
+    assert rel(got, ref.detach()) <= 1e-2
+    dx = torch.cat([x.grad.reshape(1, -1, D) for x in xs], 1)
+    assert rel(dx, xr.grad) <= 1e-2 and cosine(dx, xr.grad) >= 0.999
+    assert rel(blk.attn.proj_weight1.grad, w1.grad) <= 1e-2 and cosine(blk.attn.proj_weight1.grad, w1.grad) >= 0.999
+    assert rel(blk.attn.proj_bias1.grad, b1.grad) <= 1e-2
+
+
+@pytest.mark.parametrize("name", ["tiny_r16", "c1_vits16_r32_pert", "c2_vitb14_r8"])
+def test_model_of_fused_blocks_matches_reference_golden(name):
+    """The host model with fused blocks, driven by plain PyTorch autograd (no step engine): logits, loss and the
+    gradients of every trainable tensor against the vectors recorded from the unmodified reference."""
+    _need_gpu()
+    from apla_b200.apla import fuse_apla_blocks
+    model, meta, arr = build_case(name)
+    m = meta["meta"]
+    fuse_apla_blocks(model.cuda())
+    images, labels = synthetic_batch(m["batch"], m["img"], m["n_classes"])
+    logits = model(images.cuda())
+    loss = torch.nn.functional.cross_entropy(logits, labels.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert rel(logits.detach(), arr["s0/logits"]) <= 1e-2, rel(logits.detach(), arr["s0/logits"])
+    assert abs(float(loss) - float(arr["s0/loss"])) <= 1e-2 * abs(float(arr["s0/loss"]))
+    named = dict(model.named_parameters())
+    assert [k for k, p in named.items() if p.requires_grad] == meta["trainable"]
+    sub = m["sub"]
+    ours = torch.cat([named[k].grad.flatten()[::sub].cpu() for k in meta["trainable"]])
+    ref = torch.cat([torch.as_tensor(arr["s0/grad/" + k]).flatten() for k in meta["trainable"]])
+    assert cosine(ours, ref) >= 0.999, cosine(ours, ref)
+    assert rel(ours, ref) <= 1e-2, rel(ours, ref)
+
+
+def test_fused_block_refuses_what_it_does_not_implement():
+    _need_gpu()
+    from apla_b200.apla import FusedAplaBlock, fuse_apla_blocks
+    from apla_b200.config import AplaConfig
+    from apla_b200.hostvit import VitArch, build_classifier
+    model, _, _ = build_case("tiny_r16")
+    fuse_apla_blocks(model)
+    blk = model.backbone.blocks[0]
+    with pytest.raises(RuntimeError, match="CUDA"):
+        blk(torch.randn(1, 17, 128))                                    # no CPU fallback
+    model.cuda()
+    with pytest.raises(RuntimeError, match="probabilities"):
+        blk(torch.randn(1, 17, 128, device="cuda"), return_attention=True)
+    blk.norm1.weight.requires_grad_(True)
+    with pytest.raises(RuntimeError, match="frozen"):
+        blk(torch.randn(1, 17, 128, device="cuda"))
+    blk.norm1.weight.requires_grad_(False)
+    blk.attn.proj_drop.p = 0.1
+    blk.train()
+    with pytest.raises(RuntimeError, match="dropout"):
+        blk(torch.randn(1, 17, 128, device="cuda"))
+    # multi-GPU 'full' keeps the stock attention (apla_vit.py:65-75): nothing to fuse
+    stock = build_classifier(VitArch(128, 2, 2), img_size=56, patch_size=14, n_classes=10,
+                             apla_config=AplaConfig("full"), is_multi_gpu=True, seed=0)
+    with pytest.raises(RuntimeError, match="APLA_Attention"):
+        fuse_apla_blocks(stock)
+    with pytest.raises(TypeError):
+        FusedAplaBlock(stock.backbone.blocks[0])
