@@ -457,7 +457,7 @@ static int pick_bn(int M, int N) {
   if (N <= 128) return 128;
   const int clusters = sm_count() / 2;
   const int t256 = cdiv(M, 2 * BM) * cdiv(N, 256), t128 = cdiv(M, 2 * BM) * cdiv(N, 128);
-  const double c256 = cdiv(t256, clusters) * 1.0, c128 = cdiv(t128, clusters) * 0.54;
+  const double c256 = cdiv(t256, clusters) * 1.0, c128 = cdiv(t128, clusters) * 0.76;   // measured: 77.8 vs 51.2 us on 16448x2304x768
   return c128 < c256 ? 128 : 256;
 }
 

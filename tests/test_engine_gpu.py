@@ -226,3 +226,39 @@ def test_session_checkpoint_resume_and_reference_optimizer(tmp_path):
     sd["backbone.blocks.0.attn.inds"] = sd["backbone.blocks.0.attn.inds"].flip(0)
     with pytest.raises(RuntimeError, match="indices"):
         eng2.load_state_dict(sd)
+
+
+@pytest.mark.parametrize("dim,heads,depth,r,batch,img,layerscale", [
+    (256, 4, 2, 192, 3, 56, 1.0),        # 128 < r < dim: the dense-dY weight-gradient path with a partial row map
+    (256, 4, 2, 1, 2, 56, 1.0),          # a single trainable row
+    (128, 2, 3, 16, 1, 42, None),        # batch 1, 10 tokens, blocks without LayerScale (vit.py:272-275)
+    (128, 2, 1, 128, 5, 56, 1e-5),       # depth 1 (the pruned block 0 is also the CLS-only last block), SSL LayerScale init
+])
+def test_engine_vs_live_oracle_shapes(dim, heads, depth, r, batch, img, layerscale):
+    """Shapes and options the golden fixtures do not reach, against the oracle run live on the CPU."""
+    from oracle import apla_oracle as O
+    from apla_b200.config import AplaConfig
+    from apla_b200.hostvit import VitArch, build_classifier
+    from helpers import perturb_module
+    cfg = O.VitCfg(embed_dim=dim, depth=depth, num_heads=heads, patch_size=14, img_size=56, n_classes=10,
+                   partial_size=r, layerscale=layerscale)
+    sd = O.build_state(cfg, seed=0)
+    O.perturb_state(sd)
+    model = build_classifier(VitArch(dim, depth, heads), img_size=56, patch_size=14, n_classes=10,
+                             apla_config=AplaConfig(r), layerscale=layerscale, seed=0)
+    perturb_module(model)
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, sd[k]), k                       # same construction + perturbation on both sides
+    images, labels = synthetic_batch(batch, img, 10, seed=321)
+    ref = O.loss_and_grads(sd, cfg, images, labels)
+    eng = _engine(model, batch, img)
+    eng.forward(images.cuda(), labels.cuda())
+    eng.backward()
+    torch.cuda.synchronize()
+    assert rel(eng.logits, ref.logits) <= 1e-2, rel(eng.logits, ref.logits)
+    assert abs(float(eng.loss) - float(ref.loss)) <= 1e-2 * abs(float(ref.loss))
+    g = eng.named_grads()
+    ours = torch.cat([g[k].flatten().cpu() for k in eng.trainable_names()])
+    theirs = torch.cat([ref.grads[k].flatten() for k in eng.trainable_names()])
+    assert cosine(ours, theirs) >= 0.999, cosine(ours, theirs)
+    assert rel(ours, theirs) <= 1e-2, rel(ours, theirs)
