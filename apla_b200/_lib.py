@@ -49,6 +49,15 @@ def parse_header(path: str = HEADER) -> Dict[str, Tuple[object, List[object]]]:
     return protos
 
 
+class BlockWeights(ctypes.Structure):
+    """`apla_block_weights` of include/apla_b200.h (field for field; the library reports its sizeof for a check)."""
+    _fields_ = ([(n, ctypes.c_void_p) for n in
+                 ("wqkv", "wqkvT", "wproj", "wprojT", "wfc1", "wfc1T", "wfc2", "wfc2T",
+                  "bqkv", "bproj", "bfc1", "bfc2", "ln1w", "ln1b", "ln2w", "ln2b", "g1", "g2", "idx", "rowmap")]
+                + [(n, ctypes.c_int32) for n in ("D", "H", "hidden", "r", "r_pad")]
+                + [(n, ctypes.c_float) for n in ("eps1", "eps2", "scale")])
+
+
 class _Lib:
     def __init__(self):
         self._dll = None
@@ -66,6 +75,9 @@ class _Lib:
             fn = getattr(dll, name)          # AttributeError if the .so does not export a declared symbol
             fn.restype = restype
             fn.argtypes = argtypes
+        if dll.apla_block_weights_size() != ctypes.sizeof(BlockWeights):
+            raise RuntimeError("apla_block_weights: the ctypes mirror in apla_b200/_lib.py and the header disagree "
+                               f"({ctypes.sizeof(BlockWeights)} vs {dll.apla_block_weights_size()} bytes)")
         self._dll = dll
         return dll
 

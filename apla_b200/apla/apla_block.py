@@ -8,6 +8,7 @@ tensor-core GEMMs unless the caller wraps it in autocast.  `fuse_apla_blocks(mod
 is an `APLA_Attention` for a `FusedAplaBlock` that holds the SAME sub-modules under the SAME names (state-dict keys and
 checkpoints unchanged) and runs forward and backward through the kernels the step engine uses:
 
+  (two native calls per block and step: `apla_block_fwd`, `apla_block_bwd`, csrc/block.cu)
   forward   LN1 -> qkv GEMM -> fused attention (saves log-sum-exp) -> proj GEMM (+bias, xLayerScale, +residual, fp32)
             -> LN2 -> fc1 GEMM (+bias, GELU, saves gelu' in fp16) -> fc2 GEMM (+bias, xLayerScale, +residual, fp32)
   backward  LayerScale+cast -> fc2 dgrad x gelu' -> fc1 dgrad -> LN2' (+residual grad, xLayerScale, APLA column gather)
@@ -26,38 +27,43 @@ output has the input's dtype.  CUDA (sm_100a) only, no fallback; dropout / drop-
 """
 from __future__ import annotations
 
+import ctypes
 from typing import List, Optional, Sequence
 
 import torch
 import torch.nn as nn
 
-from .. import ops
-from .._lib import require_device
+from .._lib import LIB, BlockWeights, ptr, require_device, stream
 from .appla_attn import APLA_Attention, _pad64
 
 
 class _AplaBlockFn(torch.autograd.Function):
+    """One native call per direction (`apla_block_fwd` / `apla_block_bwd`, csrc/block.cu): 7 + up to 13 kernel launches
+    with no Python between them."""
+
     @staticmethod
     def forward(ctx, x, w1, b1, blk, cu_seqlens, seqlens):
         at = blk.attn
-        ws = at._working_set(x.device)
-        ms = blk._mlp_working_set(x.device)
-        D = x.shape[-1]
+        nat = blk._native(x.device)
+        D, H, Hd = at.dim, at.num_heads, blk.mlp.fc1.out_features
         x_in = x.reshape(-1, D).to(torch.float32).contiguous()
         T = x_in.shape[0]
         if cu_seqlens is None:
             num_seqs, max_len = (x.shape[0], x.shape[1]) if x.dim() == 3 else (1, T)
         else:
             num_seqs, max_len = len(seqlens), max(seqlens)
-        eps1, eps2 = float(blk.norm1.eps), float(blk.norm2.eps)
-        h = ops.layernorm_fwd(x_in, ms["ln1w"], ms["ln1b"], eps1)
-        qkv = ops.gemm_bias(h, ws["wqkv"], ws["bqkv"])
-        ao, lse = ops.attn_fwd(qkv, at.num_heads, float(at.scale), num_seqs, max_len, cu_seqlens=cu_seqlens)
-        x_mid = ops.gemm_bias_ls_residual(ao, ws["wproj"], ws["bproj"], ms["g1"], x_in)
-        ops.layernorm_fwd(x_mid, ms["ln2w"], ms["ln2b"], eps2, out=h)
-        dgelu, g = ops.gemm_bias_gelu_dgelu(h, ms["wfc1"], ms["bfc1"])
-        x_out = ops.gemm_bias_ls_residual(g, ms["wfc2"], ms["bfc2"], ms["g2"], x_mid)
-        ctx.blk, ctx.ws, ctx.ms = blk, ws, ms
+        dev, bf, f32 = x.device, torch.bfloat16, torch.float32
+        x_mid = torch.empty(T, D, device=dev, dtype=f32)
+        x_out = torch.empty(T, D, device=dev, dtype=f32)
+        qkv = torch.empty(T, 3 * D, device=dev, dtype=bf)
+        ao = torch.empty(T, D, device=dev, dtype=bf)
+        lse = torch.empty(T, H, device=dev, dtype=f32)
+        dgelu = torch.empty(T, Hd, device=dev, dtype=torch.float16)
+        ln_tmp = torch.empty(T, D, device=dev, dtype=bf)
+        gelu_tmp = torch.empty(T, Hd, device=dev, dtype=bf)
+        LIB.call("apla_block_fwd", ctypes.addressof(nat), ptr(x_in), ptr(x_mid), ptr(x_out), ptr(ln_tmp), ptr(qkv), ptr(ao),
+                 ptr(lse), ptr(dgelu), ptr(gelu_tmp), ptr(cu_seqlens), num_seqs, max_len, T, stream())
+        ctx.blk, ctx.nat, ctx.refs = blk, nat, blk._nat_refs      # the struct points into these tensors
         ctx.geom = (num_seqs, max_len, cu_seqlens)
         ctx.x_dtype, ctx.x_shape = x.dtype, x.shape
         ctx.save_for_backward(x_in, x_mid, qkv, ao, lse, dgelu)
@@ -65,43 +71,33 @@ class _AplaBlockFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        blk, ws, ms = ctx.blk, ctx.ws, ctx.ms
+        blk, nat = ctx.blk, ctx.nat
         at = blk.attn
         x_in, x_mid, qkv, ao, lse, dgelu = ctx.saved_tensors
         num_seqs, max_len, cu = ctx.geom
-        D = ctx.x_shape[-1]
-        r = at.partial_size
+        D, H, Hd, r = at.dim, at.num_heads, blk.mlp.fc1.out_features, at.partial_size
         want_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        want_x = ctx.needs_input_grad[0]
         dx_out = dy.reshape(-1, D).to(torch.float32).contiguous()
-        # MLP branch
-        dyb = ops.ls_cast(dx_out, ms["g2"])
-        dh = ops.gemm_dgrad_mul(dyb, ms["wfc2T"], dgelu)
-        dln = ops.gemm_dgrad(dh, ms["wfc1T"])
-        del dh
-        # dx_mid = dx_out + LN2'(dln); dyb = bf16(gamma1 * dx_mid) is the gradient at the projection output; its APLA
-        # columns are gathered in the same pass when only a few rows are trainable
-        sub = None
-        if want_w and ws["rowmap"] is None:
-            sub = torch.empty(dx_out.shape[0], _pad64(r), device=dy.device, dtype=torch.bfloat16)
-        dx_mid = ops.layernorm_bwd(dln, x_mid, ms["ln2w"], float(blk.norm2.eps), dres=dx_out, dxb=dyb, gamma=ms["g1"],
-                                   sub=sub, idx=ws["idx"] if sub is not None else None, r=r if sub is not None else 0)
-        dw1 = db1 = dx = None
+        T = dx_out.shape[0]
+        dev, bf, f32 = dy.device, torch.bfloat16, torch.float32
+        dx_mid = torch.empty(T, D, device=dev, dtype=f32)        # the input gradient lands in the same buffer
+        dyb = torch.empty(T, D, device=dev, dtype=bf)
+        dh = torch.empty(T, Hd, device=dev, dtype=bf)
+        dln = torch.empty(T, D, device=dev, dtype=bf)
+        dsub = torch.empty(T, nat.r_pad, device=dev, dtype=bf) if (want_w and not nat.rowmap) else None
+        d_ao = delta = dqkv = dw1 = db1 = None
+        if want_x:
+            d_ao = torch.empty(T, D, device=dev, dtype=bf)
+            delta = torch.empty(T, H, device=dev, dtype=f32)
+            dqkv = torch.empty(T, 3 * D, device=dev, dtype=bf)
         if want_w:
-            dw1 = torch.zeros(r, D, device=dy.device, dtype=torch.float32)
-            db1 = torch.zeros(r, device=dy.device, dtype=torch.float32)
-            if sub is None:
-                ops.proj_wgrad(dyb, ao, dw1, r, rowmap=ws["rowmap"])
-                ops.colsum(dyb, db1, D, rowmap=ws["rowmap"])
-            else:
-                ops.proj_wgrad(sub, ao, dw1, r)
-                ops.colsum(sub, db1, r)
-        if ctx.needs_input_grad[0]:
-            d_ao, delta = ops.gemm_dgrad_delta(dyb, ws["wprojT"], ao)
-            dqkv = ops.attn_bwd(qkv, None, d_ao, lse, at.num_heads, float(at.scale), num_seqs, max_len, cu_seqlens=cu,
-                                delta=delta)
-            ops.gemm_dgrad(dqkv, ws["wqkvT"], out=dln)
-            dx = ops.layernorm_bwd(dln, x_in, ms["ln1w"], float(blk.norm1.eps), dres=dx_mid, dx=dx_mid)
-            dx = dx.view(ctx.x_shape).to(ctx.x_dtype)
+            dw1 = torch.empty(r, D, device=dev, dtype=f32)       # zeroed by the library
+            db1 = torch.empty(r, device=dev, dtype=f32)
+        LIB.call("apla_block_bwd", ctypes.addressof(nat), ptr(dx_out), ptr(x_in), ptr(x_mid), ptr(qkv), ptr(ao), ptr(lse),
+                 ptr(dgelu), ptr(dx_mid), ptr(dx_mid) if want_x else None, ptr(dyb), ptr(dh), ptr(dln), ptr(dsub), ptr(d_ao),
+                 ptr(delta), ptr(dqkv), ptr(dw1), ptr(db1), ptr(cu), num_seqs, max_len, T, stream())
+        dx = dx_mid.view(ctx.x_shape).to(ctx.x_dtype) if want_x else None
         return dx, dw1, db1, None, None, None
 
 
@@ -168,6 +164,26 @@ class FusedAplaBlock(nn.Module):
                     ln2w=dev(self.norm2.weight, f32), ln2b=dev(self.norm2.bias, f32), g1=dev(g1, f32), g2=dev(g2, f32))
             self._ms_key = key
         return self._ms
+
+    def _native(self, device) -> BlockWeights:
+        """The `apla_block_weights` struct over the two working sets (rebuilt only when one of them was)."""
+        at = self.attn
+        ws = at._working_set(device)          # also re-scatters proj_weight1 / proj_bias1 when they changed
+        ms = self._mlp_working_set(device)
+        key = (id(ws), id(ms))
+        if getattr(self, "_nat_key", None) != key:
+            r = at.partial_size
+            fields = dict(ws)
+            fields.update(ms)
+            nat = BlockWeights()
+            for name in ("wqkv", "wqkvT", "wproj", "wprojT", "wfc1", "wfc1T", "wfc2", "wfc2T", "bqkv", "bproj", "bfc1",
+                         "bfc2", "ln1w", "ln1b", "ln2w", "ln2b", "g1", "g2", "rowmap"):
+                setattr(nat, name, ptr(fields[name]))
+            nat.idx = ptr(ws["idx"]) if ws["rowmap"] is None else None
+            nat.D, nat.H, nat.hidden, nat.r, nat.r_pad = at.dim, at.num_heads, self.mlp.fc1.out_features, r, _pad64(r)
+            nat.eps1, nat.eps2, nat.scale = float(self.norm1.eps), float(self.norm2.eps), float(at.scale)
+            self._nat, self._nat_key, self._nat_refs = nat, key, (ws, ms)
+        return self._nat
 
     def _check(self, x):
         if not x.is_cuda:

@@ -149,6 +149,35 @@ int apla_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, int
 int apla_proj_refresh(const float* w1, const float* b1, const int32_t* idx, void* wfull, void* wfullT, float* bfull,
                       int L, int r, int D, int64_t w1_block_stride, int64_t b1_block_stride, apla_stream_t stream);
 
+/* --- one block, two calls -------------------------------------------------------------------------------- */
+/* Block.forward (src/utils/transformers/vit.py:279-288: x += ls1(attn(norm1(x))); x += ls2(mlp(norm2(x)))) around an
+ * APLA attention (src/apla/appla_attn.py:50-83) and its backward, as the launch sequences the step engine runs per
+ * block.  cu_seqlens != NULL: packed crops, block-diagonal attention (dinov2/layers/block.py:274-288).
+ * Weights: bf16 [out,in] and pre-transposed [in,out] copies of the frozen Linears, the dense projection copy with the
+ * trainable rows scattered in (apla_proj_refresh), fp32 biases / LayerNorm / LayerScale vectors (g1, g2 NULL = none).
+ * idx: the r trainable rows (compact path, r <= 128, r_pad = r rounded up to 64); rowmap: int32[D] row -> slot of dW1
+ * or -1 (dense path); exactly one of the two is set when a weight gradient is requested. */
+typedef struct apla_block_weights {
+  const void *wqkv, *wqkvT, *wproj, *wprojT, *wfc1, *wfc1T, *wfc2, *wfc2T;
+  const float *bqkv, *bproj, *bfc1, *bfc2, *ln1w, *ln1b, *ln2w, *ln2b, *g1, *g2;
+  const int32_t *idx, *rowmap;
+  int32_t D, H, hidden, r, r_pad;
+  float eps1, eps2, scale;
+} apla_block_weights;
+int apla_block_weights_size(void);
+/* x_in f32[T,D] -> x_mid f32[T,D] (after the attention branch) -> x_out f32[T,D]; saves qkv bf16[T,3D], ao bf16[T,D],
+ * lse f32[T,H], dgelu f16[T,hidden] for backward; ln_tmp bf16[T,D] and gelu_tmp bf16[T,hidden] are scratch. */
+int apla_block_fwd(const apla_block_weights* w, const float* x_in, float* x_mid, float* x_out, void* ln_tmp, void* qkv,
+                   void* ao, float* lse, void* dgelu, void* gelu_tmp, const int32_t* cu_seqlens, int num_seqs,
+                   int max_seqlen, int T, apla_stream_t stream);
+/* dx_out f32[T,D] -> dx_in f32[T,D] (NULL: no input gradient wanted; may alias dx_mid) and dw1 f32[r,D] / db1 f32[r]
+ * (NULL: no weight gradient; zeroed here).  dx_mid f32[T,D], dyb bf16[T,D], dh bf16[T,hidden], dln bf16[T,D],
+ * dsub bf16[T,r_pad] (compact path), d_ao bf16[T,D], delta f32[T,H], dqkv bf16[T,3D] are scratch. */
+int apla_block_bwd(const apla_block_weights* w, const float* dx_out, const float* x_in, const float* x_mid,
+                   const void* qkv, const void* ao, const float* lse, const void* dgelu, float* dx_mid, float* dx_in,
+                   void* dyb, void* dh, void* dln, void* dsub, void* d_ao, float* delta, void* dqkv, float* dw1,
+                   float* db1, const int32_t* cu_seqlens, int num_seqs, int max_seqlen, int T, apla_stream_t stream);
+
 /* --- step engine: the whole fine-tune step as one native call sequence ------------------------------------ */
 /* Replaces Trainer.global_step's device work (src/defaults/trainer.py:106-138): Classifier.forward
  * (src/defaults/models.py:81-92), CrossEntropyLoss, loss.backward() restricted to the APLA rows + head,
