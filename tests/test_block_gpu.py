@@ -72,23 +72,25 @@ def test_fused_block_matches_oracle_dense(name, l, B, N):
     assert rel(at.proj_weight1.grad, w1.grad) <= 1e-2
 
 
-def test_fused_block_packed_crops():
+@pytest.mark.parametrize("name,l,n_global,n_local", [("tiny_r16", 1, 2, 4),
+                                                     ("vitl14_r128", 10, 2, 8)])      # C4: ViT-L, 2 global + 8 local crops
+def test_fused_block_packed_crops(name, l, n_global, n_local):
     """dinov2 multi-crop: a list of [b_i, N_i, D] crop tensors is packed and attended block-diagonally; every crop's
     tokens get gradients (iBOT / dense losses), the projection rows get one summed weight gradient."""
     _need_gpu()
     from apla_b200.apla import fuse_apla_blocks
-    model, _, _ = build_case("tiny_r16")
+    model, _, _ = build_case(name)
     D = model.backbone.embed_dim
     g = torch.Generator().manual_seed(5)
-    crops = [torch.randn(2, 257, D, generator=g), torch.randn(4, 50, D, generator=g)]
+    crops = [torch.randn(n_global, 257, D, generator=g), torch.randn(n_local, 50, D, generator=g)]
     dys = [torch.randn(c.shape, generator=g) for c in crops]
-    seqlens = [257, 257, 50, 50, 50, 50]
+    seqlens = [257] * n_global + [50] * n_local
     packed = torch.cat([c.reshape(1, -1, D) for c in crops], 1)
-    ref, xr, w1, b1 = _oracle_block(model, 1, packed, seqlens)
+    ref, xr, w1, b1 = _oracle_block(model, l, packed, seqlens)
     ref.backward(torch.cat([d.reshape(1, -1, D) for d in dys], 1))
 
     fuse_apla_blocks(model.cuda())
-    blk = model.backbone.blocks[1]
+    blk = model.backbone.blocks[l]
     xs = [c.cuda().requires_grad_(True) for c in crops]
     outs = blk(xs)
     assert isinstance(outs, list) and [o.shape for o in outs] == [c.shape for c in crops]

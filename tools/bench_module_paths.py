@@ -63,6 +63,53 @@ def run(name, model, B, steps, warmup, autocast):
     torch.cuda.reset_peak_memory_stats()
 
 
+def run_c4_backbone(images_n, steps, warmup):
+    """C4's block path: the DINOv2 student's 24 ViT-L/14 blocks over packed multi-crop input (2 global 224-px crops =
+    257 tokens and 8 local 98-px crops = 50 tokens per image, ISIC2019 config) forward + backward through the fused
+    blocks (partial_size = dim: every projection row trainable, the SSL configs' 'full'), and the teacher's forward over
+    the global crops.  Heads, losses and the patch embedding are outside SURVEY 8 (row f2): the loss gradient is a
+    random tensor.  Prints crops-per-second and the algorithmic TFLOP/s of the block path."""
+    m = build_classifier("vit_large", apla_config=AplaConfig(1024), img_size=518, patch_size=14, n_classes=8, seed=0)
+    fuse_apla_blocks(m.cuda())
+    blocks = m.backbone.blocks
+    D, L = 1024, len(blocks)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    glob = torch.randn(2 * images_n, 257, D, device="cuda", generator=g)
+    loc = torch.randn(8 * images_n, 50, D, device="cuda", generator=g)
+    dg, dl = torch.randn_like(glob) * 1e-3, torch.randn_like(loc) * 1e-3
+
+    def step():
+        for p in m.parameters():
+            p.grad = None
+        xs = [glob.clone().requires_grad_(True), loc.clone().requires_grad_(True)]     # tokens after a trainable-free embed
+        for blk in blocks:
+            xs = blk(xs)
+        torch.autograd.backward(xs, [dg, dl])
+        with torch.no_grad():                       # teacher: forward only, global crops
+            t = glob
+            for blk in blocks:
+                t = blk(t)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    lin = 24 * D * D
+    tok = lambda n, cnt: cnt * n * (lin + 4 * n * D)                                   # noqa: E731  forward FLOPs
+    f_student = tok(257, 2 * images_n) + tok(50, 8 * images_n)
+    b_student = sum(cnt * n * (lin + 2.5 * 4 * n * D + 2 * D * D) for n, cnt in ((257, 2 * images_n), (50, 8 * images_n)))
+    flops = L * (f_student + b_student + tok(257, 2 * images_n))
+    print(json.dumps(dict(path="c4_block_path_vitl", images=images_n, student_tokens=2 * images_n * 257 + 8 * images_n * 50,
+                          teacher_tokens=2 * images_n * 257, ms_per_step=ms, images_per_s=images_n / ms * 1e3,
+                          tflops=flops / ms / 1e9, peak_mem_gb=torch.cuda.max_memory_allocated() / 1e9)), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=64)
@@ -78,6 +125,9 @@ def main():
         elif p == "attn_only":
             m = build_classifier("vit_base", apla_config=AplaConfig(8), **kw)
             run(p, m, a.batch, a.steps, a.warmup, autocast=True)
+        elif p == "c4":
+            run_c4_backbone(a.batch, a.steps, a.warmup)
+            continue
         elif p in ("fused_block", "fused_block_r768"):
             m = build_classifier("vit_base", apla_config=AplaConfig(768 if p.endswith("768") else 8), **kw)
             run(p, fuse_apla_blocks(m), a.batch, a.steps, a.warmup, autocast=False)
