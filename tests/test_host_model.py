@@ -92,3 +92,37 @@ def test_varlen_mask_helper():
     assert _seqlens_of(FakeX()) == [3, 7]
     with pytest.raises(AssertionError):
         _seqlens_of(object())
+
+
+def test_fuse_apla_blocks_host_logic():
+    """Block-level drop-in, the part that needs no GPU: the swap keeps every state-dict key and parameter object, is
+    idempotent, refuses models without APLA attention, and the fused block has no CPU path."""
+    import ctypes
+    from apla_b200._lib import LIB, BlockWeights
+    from apla_b200.apla import FusedAplaBlock, fuse_apla_blocks
+    from apla_b200.hostvit import VitArch, build_classifier
+    model, meta, _ = build_case("tiny_r16")
+    keys = list(model.state_dict().keys())
+    params = {n: id(p) for n, p in model.named_parameters()}
+    assert fuse_apla_blocks(model) is model
+    assert all(isinstance(b, FusedAplaBlock) for b in model.backbone.blocks)
+    assert list(model.state_dict().keys()) == keys == meta["state_keys"]
+    assert {n: id(p) for n, p in model.named_parameters()} == params
+    assert [n for n, p in model.named_parameters() if p.requires_grad] == meta["trainable"]
+    fuse_apla_blocks(model)                                                       # second call: nothing left to swap
+    assert list(model.state_dict().keys()) == keys
+    model.float()                                                                 # nn.Module._apply still reaches the children
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.backbone.blocks[0](torch.randn(1, 17, 128))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.backbone.blocks[0]([torch.randn(1, 17, 128), torch.randn(2, 5, 128)])
+    with pytest.raises(AssertionError):
+        model.backbone.blocks[0]([])
+    stock = build_classifier(VitArch(128, 2, 2), img_size=56, patch_size=14, n_classes=10,
+                             apla_config=AplaConfig("full"), is_multi_gpu=True, seed=0)
+    with pytest.raises(RuntimeError, match="APLA_Attention"):
+        fuse_apla_blocks(stock)
+    with pytest.raises(AttributeError):
+        fuse_apla_blocks(torch.nn.Linear(2, 2))
+    # the ctypes mirror of apla_block_weights is the size the library was compiled with
+    assert LIB.load().apla_block_weights_size() == ctypes.sizeof(BlockWeights)
