@@ -340,11 +340,18 @@ class FineTuneEngine:
 
     def save_session(self, path: str, *, iters: Optional[int] = None, epoch: int = 0, parameters=None,
                      best_val_target=None, original_state=None) -> str:
-        """Write `<path>` in the reference's session format (bases.py:448-468)."""
+        """Write `<path>` in the reference's session format (bases.py:448-468).  Data parallel: rank 0 writes (every
+        rank holds the same parameters and moments), then all ranks meet, as the reference does (`if self.is_rank0`
+        ... `synchronize()`, bases.py:453,467)."""
         from .checkpoint import save_session
-        return save_session(path, state_dict=self.state_dict(), optimizer=self.optimizer_state_dict(),
-                            iters=self.step_count if iters is None else iters, epoch=epoch, parameters=parameters,
-                            best_val_target=best_val_target, original_state=original_state)
+        dist_on = self._dist_on() and self.world > 1
+        if not dist_on or torch.distributed.get_rank(self.pg) == 0:
+            save_session(path, state_dict=self.state_dict(), optimizer=self.optimizer_state_dict(),
+                         iters=self.step_count if iters is None else iters, epoch=epoch, parameters=parameters,
+                         best_val_target=best_val_target, original_state=original_state)
+        if dist_on:
+            torch.distributed.barrier(self.pg)
+        return path
 
     def load_session(self, path: str, restore_only_model: bool = False) -> dict:
         """bases.py:405-433: model tensors, then (unless restore_only_model) iters / epoch / optimiser state.
