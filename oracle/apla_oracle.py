@@ -20,7 +20,9 @@ Pinning: ``tests/golden/make_golden.py`` imports the UNMODIFIED reference from
 loss, gradients and post-step parameters; ``tests/test_oracle_golden.py`` replays them against
 this file (bit-exact indices / weights, <=1e-5 relative on floats).  Parity is therefore
 *pinned* for configs C1, C2, C3, C5 shapes; the varlen (xformers) path of C4 is restated from
-the call sites only and is "parity unpinned" (xformers is not available).
+the call sites (xformers is not available) and pinned MODULO A PLAIN-TORCH XFORMERS
+SHIM by tests/golden/make_golden_ssl_step.py, which runs the reference's packed multi-crop blocks
+through it (tests/test_ssl_oracle.py::test_ssl_step_matches_reference).
 
 Reference citations are relative to /root/reference/.
 """
@@ -240,8 +242,8 @@ def softmax_attention(qkv: Tensor, B: int, N: int, H: int, scale: float) -> Tupl
 def varlen_attention(qkv: Tensor, seqlens: Sequence[int], H: int, scale: float) -> Tensor:
     """Restatement of xformers memory_efficient_attention with a BlockDiagonalMask
     (appla_attn_mem_eff.py:37-43; dinov2/layers/block.py:191-217): independent softmax
-    attention per original sequence of the packed [1, sum(N), 3D] tensor.  PARITY UNPINNED
-    (xformers 0.0.18 is absent from this image and from /root/reference)."""
+    attention per original sequence of the packed [1, sum(N), 3D] tensor.  Pinned modulo the
+    xformers shim (module docstring): xformers 0.0.18 itself is absent from this image and /root/reference."""
     outs, o = [], 0
     for n in seqlens:
         out, _ = softmax_attention(qkv[:, o:o + n], 1, n, H, scale)

@@ -21,14 +21,19 @@ Plain fp32 PyTorch-on-CPU restatement (functional, weights in flat dicts keyed l
 Pinning: ``tests/golden/make_golden_ssl.py`` loads the four reference files above BY PATH (their package ``__init__``
 imports xformers, which this image lacks) and records head outputs, teacher targets, the three losses, their
 gradients and the centre updates; ``tests/test_ssl_oracle.py`` replays them against this file (<= 1e-5 relative).
-Those components are therefore *pinned*.  ``ssl_objective`` (the assembly in ``models.py``, which cannot be imported
-without xformers) is restated from the source with every scale cited -- **assembly parity unpinned**; so is the
-xformers ``cross_entropy`` the reference prefers for the iBOT term when xformers is present (the fallback it defines
-itself, ibot_patch_loss.py:26-27, is what is pinned; the two are the same function of their inputs).
+Those components are therefore *pinned*.  The whole step -- ``ssl_step``: teacher backbone on the unmasked global crops,
+student backbone over the packed [masked global | local] crop list, ``ssl_objective``, ``ema_update`` -- is pinned against
+``DINOv2.forward`` / ``update_teacher`` of the UNMODIFIED reference run on the CPU for two steps
+(``tests/golden/make_golden_ssl_step.py`` -> ``ssl_step_tiny``; loss, the four loss terms, every trainable gradient, the
+teacher after the EMA and both centres, <= 2e-5).  The reference's ``models.py`` cannot be imported without xformers, so
+that generator supplies ``tests/golden/xformers_shim.py`` (plain-torch ``memory_efficient_attention``, ``unbind``,
+``BlockDiagonalMask``): **pinned modulo the xformers shim** -- the kernels of xformers 0.0.18 themselves and its
+``cross_entropy`` (the reference's own fallback, ibot_patch_loss.py:26-27, is what ran) are the unpinned residue.
 Sinkhorn-Knopp centring (dino_clstoken_loss.py:33-60) is not restated: every shipped config uses "centering".
 """
 from __future__ import annotations
 
+import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -148,7 +153,7 @@ def ssl_objective(student_head: Dict[str, Tensor], teacher_head: Dict[str, Tenso
                   teacher_temp: float, n_local_crops: int = 8, n_global_crops: int = 2, dino_loss_weight: float = 1.0,
                   koleo_loss_weight: float = 0.1, ibot_loss_weight: float = 1.0, student_temp: float = 0.1,
                   center_momentum: float = 0.9, world_size: int = 1):
-    """ASSEMBLY PARITY UNPINNED (see the module docstring).  Inputs are backbone outputs after the final norm:
+    """Pinned through ``ssl_step`` (see the module docstring).  Inputs are backbone outputs after the final norm:
     student_local_cls [n_local*B, D], student_global_cls [2B, D], student_global_patch [2B, P, D], the teacher's
     [2B, D] / [2B, P, D] on the same global crops, masks bool [2B, P].  -> (loss, loss_dict, new centres)."""
     assert n_global_crops == 2                                                            # :214
@@ -207,3 +212,97 @@ def ema_update(teacher: Dict[str, Tensor], student: Dict[str, Tensor], m: float)
         for k, t in teacher.items():
             if t.is_floating_point() and k in student:
                 t.mul_(m).add_(student[k].detach(), alpha=1 - m)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the backbone as the SSL step drives it (DinoVisionTransformer, dinov2_vits.py) and the whole step
+# ---------------------------------------------------------------------------------------------------------------------
+def dinov2_pos_embed(pos_embed: Tensor, w: int, h: int, patch: int, interpolate_offset: float = 0.1,
+                     antialias: bool = False) -> Tensor:
+    """dinov2_vits.py:176-208: bicubic resize of the patch grid of the table to (w // patch, h // patch); with the
+    shipped ``interpolate_offset`` 0.1 the resize is driven by scale factors (w0 + 0.1) / M, not by the output size."""
+    N = pos_embed.shape[1] - 1
+    w0, h0 = w // patch, h // patch
+    if w0 * h0 == N and w == h:
+        return pos_embed
+    M = int(math.sqrt(N))
+    assert N == M * M
+    dim = pos_embed.shape[-1]
+    grid = pos_embed[:, 1:].float().reshape(1, M, M, dim).permute(0, 3, 1, 2)
+    if interpolate_offset:
+        kw = dict(scale_factor=(float(w0 + interpolate_offset) / M, float(h0 + interpolate_offset) / M))
+    else:
+        kw = dict(size=(w0, h0))
+    grid = F.interpolate(grid, mode="bicubic", antialias=antialias, **kw)
+    assert (w0, h0) == tuple(grid.shape[-2:])
+    return torch.cat((pos_embed[:, :1].float(), grid.permute(0, 2, 3, 1).reshape(1, -1, dim)), dim=1)
+
+
+def dinov2_prepare_tokens(sd: Dict[str, Tensor], images: Tensor, masks: Optional[Tensor], patch: int,
+                          pre: str = "backbone.") -> Tensor:
+    """dinov2_vits.py:210-231 (no register tokens in any shipped config): patch embedding, masked patches replaced by
+    ``mask_token`` BEFORE the position table is added, CLS token prepended."""
+    _, _, w, h = images.shape
+    x = F.conv2d(images, sd[pre + "patch_embed.proj.weight"], sd[pre + "patch_embed.proj.bias"], stride=patch)
+    x = x.flatten(2).transpose(1, 2)
+    if masks is not None:
+        x = torch.where(masks.unsqueeze(-1), sd[pre + "mask_token"].to(x.dtype).unsqueeze(0), x)
+    x = torch.cat((sd[pre + "cls_token"].expand(x.shape[0], -1, -1), x), dim=1)
+    return x + dinov2_pos_embed(sd[pre + "pos_embed"], w, h, patch)
+
+
+def dinov2_backbone(sd: Dict[str, Tensor], crops, masks, *, patch: int, depth: int, num_heads: int,
+                    eps: float = 1e-6, pre: str = "backbone."):
+    """``DinoVisionTransformer.forward_features`` (dinov2_vits.py:269-289) for one tensor of crops, or
+    ``forward_features_list`` (:249-267) for a list: every block then runs ONCE over the crops of all resolutions packed
+    into one [1, sum b_i n_i, D] sequence under a block-diagonal mask (layers/block.py:244-288 -- attention per original
+    sequence, everything else token-wise), and the final LayerNorm is applied per resolution.
+    -> dict(cls [b, D], patch [b, P, D]) or a list of them."""
+    from oracle.apla_oracle import block_forward
+    is_list = isinstance(crops, (list, tuple))
+    xs = [dinov2_prepare_tokens(sd, c, m, patch, pre) for c, m in zip(crops, masks)] if is_list \
+        else [dinov2_prepare_tokens(sd, crops, masks, patch, pre)]
+    D = xs[0].shape[-1]
+    if is_list:
+        seqlens = [x.shape[1] for x in xs for _ in range(x.shape[0])]
+        packed = torch.cat([x.reshape(1, -1, D) for x in xs], dim=1)
+        for i in range(depth):
+            packed = block_forward(sd, f"{pre}blocks.{i}.", packed, num_heads, eps, seqlens=seqlens)
+        outs, o = [], 0
+        for x in xs:
+            n = x.shape[0] * x.shape[1]
+            outs.append(packed[:, o:o + n].reshape(x.shape))
+            o += n
+    else:
+        x = xs[0]
+        for i in range(depth):
+            x = block_forward(sd, f"{pre}blocks.{i}.", x, num_heads, eps)
+        outs = [x]
+    res = []
+    for x in outs:
+        xn = F.layer_norm(x, (D,), sd[pre + "norm.weight"], sd[pre + "norm.bias"], eps)
+        res.append(dict(cls=xn[:, 0], patch=xn[:, 1:]))
+    return res if is_list else res[0]
+
+
+def ssl_step(student: Dict[str, Tensor], teacher: Dict[str, Tensor], global_crops: Tensor, local_crops: Tensor,
+             masks: Tensor, dino_center: Tensor, ibot_center: Tensor, *, teacher_temp: float, patch: int, depth: int,
+             num_heads: int, n_local_crops: int = 8, n_global_crops: int = 2, dino_loss_weight: float = 1.0,
+             koleo_loss_weight: float = 0.1, ibot_loss_weight: float = 1.0, center_momentum: float = 0.9,
+             world_size: int = 1):
+    """``DINOv2.forward`` end to end (models.py:207-433): the teacher backbone sees the global crops UNMASKED as one
+    plain batch (:240), the student backbone sees [global crops with masks, local crops] as a packed list (:322-324);
+    then ``ssl_objective``.  ``student`` / ``teacher`` are flat state dicts (``backbone.*``, ``dino_head.*``).
+    PINNED against the unmodified reference modulo the xformers shim (tests/golden/make_golden_ssl_step.py).
+    -> (loss, loss_dict, (dino_center, ibot_center) for the next step)."""
+    kw = dict(patch=patch, depth=depth, num_heads=num_heads)
+    with torch.no_grad():
+        t = dinov2_backbone(teacher, global_crops, None, **kw)
+    s_glob, s_loc = dinov2_backbone(student, [global_crops, local_crops], [masks, None], **kw)
+    head = lambda sd: {k[len("dino_head."):]: v for k, v in sd.items() if k.startswith("dino_head.")}  # noqa: E731
+    return ssl_objective(head(student), head(teacher), student_local_cls=s_loc["cls"], student_global_cls=s_glob["cls"],
+                         student_global_patch=s_glob["patch"], teacher_global_cls=t["cls"],
+                         teacher_global_patch=t["patch"], masks=masks, dino_center=dino_center, ibot_center=ibot_center,
+                         teacher_temp=teacher_temp, n_local_crops=n_local_crops, n_global_crops=n_global_crops,
+                         dino_loss_weight=dino_loss_weight, koleo_loss_weight=koleo_loss_weight,
+                         ibot_loss_weight=ibot_loss_weight, center_momentum=center_momentum, world_size=world_size)

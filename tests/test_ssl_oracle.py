@@ -118,3 +118,66 @@ def test_weight_norm_matches_torch():
         lin.weight_g.mul_(torch.rand(5, 1) + 0.5)
     x = torch.randn(4, 7)
     assert torch.allclose(torch.nn.functional.linear(x, S.weight_norm_weight(lin.weight_g, lin.weight_v)), lin(x), atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the whole self-supervised step, pinned against the UNMODIFIED reference (tests/golden/make_golden_ssl_step.py runs
+# DINOv2.forward / update_teacher on the CPU through tests/golden/xformers_shim.py: "pinned modulo the xformers shim")
+# ---------------------------------------------------------------------------------------------------------------------
+def _seeded_fill(shapes, int_arrays, seed):
+    """The generator's `seeded_fill`: floating tensors in sorted key order from one torch.Generator."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k in sorted(shapes):
+        if k in int_arrays:
+            sd[k] = torch.as_tensor(int_arrays[k])
+            continue
+        n = torch.randn(shapes[k], generator=g)
+        gain = k.endswith(("norm.weight", "norm1.weight", "norm2.weight", ".gamma", "weight_g"))
+        sd[k] = 1.0 + 0.1 * n if gain else 0.05 * n
+    return sd
+
+
+def test_ssl_step_matches_reference(golden_dir):
+    with open(os.path.join(golden_dir, "ssl_step_tiny.json")) as f:
+        meta = json.load(f)
+    arr = np.load(os.path.join(golden_dir, "ssl_step_tiny.npz"))
+    cfg = meta["cfg"]
+    ints = lambda who: {k[len(who) + 5:]: arr[k] for k in arr.files if k.startswith(who + "_int/")}    # noqa: E731
+    student = _seeded_fill(meta["student_keys"], ints("student"), 11)
+    teacher = _seeded_fill(meta["teacher_keys"], ints("teacher"), 12)
+    # the reference builds the teacher as its own model and then loads the student's state dict into it, buffers
+    # included (models.py:138): same column indices on both sides, bit for bit
+    for k, v in ints("student").items():
+        assert np.array_equal(v, ints("teacher")[k])
+    assert meta["teacher_trainable"] == []
+    trainable = meta["trainable"]
+    assert all(("proj_weight1" in n or "proj_bias1" in n or n.startswith("dino_head.")) for n in trainable)
+    for n in trainable:
+        student[n].requires_grad_(True)
+    glob, loc = torch.as_tensor(arr["in/global"]), torch.as_tensor(arr["in/local"])
+    masks = torch.as_tensor(arr["in/masks"])
+    dino_c, ibot_c = torch.zeros(1, cfg["K"]), torch.zeros(1, 1, cfg["K"])
+    for step in range(2):
+        tag = f"s{step}/"
+        for n in trainable:
+            student[n].grad = None
+        loss, parts, (dino_c, ibot_c) = S.ssl_step(
+            student, teacher, glob, loc, masks, dino_c, ibot_c, teacher_temp=cfg["teacher_temp"], patch=cfg["patch"],
+            depth=cfg["depth"], num_heads=cfg["num_heads"], n_local_crops=cfg["n_local"],
+            n_global_crops=cfg["n_global"], dino_loss_weight=cfg["dino_w"], koleo_loss_weight=cfg["koleo_w"],
+            ibot_loss_weight=cfg["ibot_w"])
+        loss.backward()
+        assert rel(loss.detach(), arr[tag + "loss"]) < 1e-5, (step, float(loss), float(arr[tag + "loss"]))
+        for k in ("dino_local_crops_loss", "dino_global_crops_loss", "koleo_loss", "ibot_loss"):
+            assert rel(parts[k].detach(), arr[tag + "loss/" + k]) < 1e-5, (step, k)
+        for n in trainable:
+            assert rel(student[n].grad, arr[tag + "grad/" + n]) < 2e-5, (step, n, rel(student[n].grad, arr[tag + "grad/" + n]))
+        S.ema_update(teacher, student, cfg["momentum"])
+        with torch.no_grad():
+            for n in trainable:
+                student[n].add_(student[n].grad, alpha=-0.05)
+        for k in ("backbone.blocks.1.attn.proj_weight1", "dino_head.mlp.0.weight"):
+            assert rel(teacher[k], arr[tag + "teacher_after/" + k]) < 1e-6, (step, k)
+    assert rel(dino_c, arr["final/dino_center"]) < 1e-5
+    assert rel(ibot_c, arr["final/ibot_center"]) < 1e-5
