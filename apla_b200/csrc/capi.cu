@@ -142,4 +142,61 @@ int apla_proj_refresh(const float* w1, const float* b1, const int32_t* idx, void
   return proj_refresh(w1, b1, idx, wfull, wfullT, bfull, L, r, D, w1_block_stride, b1_block_stride, S(stream));
 }
 
+// --- DINOv2 self-supervised objective (ssl.cu) ---
+int apla_softmax_center(const float* t, int64_t ldt, const float* center, float inv_temp, int rows, int K, float* out,
+                        int64_t ldo, apla_stream_t stream) {
+  return ssl_softmax_center(t, ldt, center, inv_temp, rows, K, out, ldo, S(stream));
+}
+int apla_colsum_f32(const float* a, int64_t ld, int rows, int K, float* ws, int splits, float scale, float* out,
+                    apla_stream_t stream) {
+  return ssl_colsum_f32(a, ld, rows, K, ws, splits, scale, out, S(stream));
+}
+int apla_center_ema(float* center, const float* batch_sum, int K, float inv_count, float momentum,
+                    apla_stream_t stream) {
+  return ssl_center_ema(center, batch_sum, K, inv_count, momentum, S(stream));
+}
+int apla_soft_ce_fwd(const float* s, int64_t lds, int rows, int K, const float* t0, const float* t1, int64_t ldt,
+                     int t_rows, const float* w_row, float w_uniform, float inv_temp, float* row_loss, float* lse,
+                     float* mass, apla_stream_t stream) {
+  return ssl_soft_ce_fwd(s, lds, rows, K, t0, t1, ldt, t_rows, w_row, w_uniform, inv_temp, row_loss, lse, mass,
+                         S(stream));
+}
+int apla_soft_ce_bwd(const float* s, int64_t lds, int rows, int K, const float* t0, const float* t1, int64_t ldt,
+                     int t_rows, const float* w_row, float w_uniform, float inv_temp, const float* lse,
+                     const float* mass, const float* gscale, void* ds, int64_t ldd, int ds_is_bf16,
+                     apla_stream_t stream) {
+  return ssl_soft_ce_bwd(s, lds, rows, K, t0, t1, ldt, t_rows, w_row, w_uniform, inv_temp, lse, mass, gscale, ds, ldd,
+                         ds_is_bf16, S(stream));
+}
+int apla_sum_f32(const float* a, int n, float scale, float* out, apla_stream_t stream) {
+  return ssl_sum_f32(a, n, scale, out, S(stream));
+}
+int apla_l2norm_fwd(const void* x, int64_t ldx, int x_is_f32, int rows, int d, float eps, void* y_bf16, float* y_f32,
+                    int64_t ldy, apla_stream_t stream) {
+  return ssl_l2norm_fwd(x, ldx, x_is_f32, rows, d, eps, y_bf16, y_f32, ldy, S(stream));
+}
+int apla_l2norm_bwd(const void* x, int64_t ldx, int x_is_f32, const void* dy, int64_t ld_dy, int grads_are_f32,
+                    int rows, int d, float eps, void* dx, int64_t ld_dx, apla_stream_t stream) {
+  return ssl_l2norm_bwd(x, ldx, x_is_f32, dy, ld_dy, grads_are_f32, rows, d, eps, dx, ld_dx, S(stream));
+}
+int apla_weightnorm_fwd(const float* g, const float* v, int K, int d, void* w_bf16, float* w_f32,
+                        apla_stream_t stream) {
+  return ssl_weightnorm_fwd(g, v, K, d, w_bf16, w_f32, S(stream));
+}
+int apla_weightnorm_bwd(const float* g, const float* v, const float* dW, int64_t ld_dw, int K, int d, float* dg,
+                        float* dv, apla_stream_t stream) {
+  return ssl_weightnorm_bwd(g, v, dW, ld_dw, K, d, dg, dv, S(stream));
+}
+int apla_koleo_fwd(const float* xn, int groups, int n, int D, float eps, float w, int32_t* nn, float* dist,
+                   float* row_loss, apla_stream_t stream) {
+  return ssl_koleo_fwd(xn, groups, n, D, eps, w, nn, dist, row_loss, S(stream));
+}
+int apla_koleo_bwd(const float* x, const float* xn, int groups, int n, int D, float eps, float norm_eps, float w,
+                   const int32_t* nn, const float* dist, const float* gscale, float* dx, apla_stream_t stream) {
+  return ssl_koleo_bwd(x, xn, groups, n, D, eps, norm_eps, w, nn, dist, gscale, dx, S(stream));
+}
+int apla_ema_update(float* teacher, const float* student, int64_t n, float m, apla_stream_t stream) {
+  return ssl_ema(teacher, student, n, m, S(stream));
+}
+
 }  // extern "C"

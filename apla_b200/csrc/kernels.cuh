@@ -70,4 +70,30 @@ int adamw_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t 
 int proj_refresh(const float* w1, const float* b1, const int* idx, void* wfull, void* wfullT, float* bfull, int L,
                  int r, int D, int64_t w1_block_stride, int64_t b1_block_stride, cudaStream_t s);
 
+// ssl.cu: row kernels of the DINOv2 self-supervised objective
+int ssl_softmax_center(const float* t, int64_t ldt, const float* center, float inv_temp, int rows, int K, float* out,
+                       int64_t ldo, cudaStream_t s);
+int ssl_colsum_f32(const float* a, int64_t ld, int rows, int K, float* ws, int splits, float scale, float* out,
+                   cudaStream_t s);
+int ssl_center_ema(float* center, const float* batch_sum, int K, float inv_count, float momentum, cudaStream_t s);
+int ssl_soft_ce_fwd(const float* sp, int64_t lds, int rows, int K, const float* t0, const float* t1, int64_t ldt,
+                    int t_rows, const float* w_row, float w_uniform, float inv_temp, float* row_loss, float* lse,
+                    float* mass, cudaStream_t s);
+int ssl_soft_ce_bwd(const float* sp, int64_t lds, int rows, int K, const float* t0, const float* t1, int64_t ldt,
+                    int t_rows, const float* w_row, float w_uniform, float inv_temp, const float* lse, const float* mass,
+                    const float* gscale, void* ds, int64_t ldd, int ds_is_bf16, cudaStream_t s);
+int ssl_sum_f32(const float* a, int n, float scale, float* out, cudaStream_t s);
+int ssl_l2norm_fwd(const void* x, int64_t ldx, int x_is_f32, int rows, int d, float eps, void* y_bf16, float* y_f32,
+                   int64_t ldy, cudaStream_t s);
+int ssl_l2norm_bwd(const void* x, int64_t ldx, int x_is_f32, const void* dy, int64_t ld_dy, int grads_are_f32, int rows,
+                   int d, float eps, void* dx, int64_t ld_dx, cudaStream_t s);
+int ssl_weightnorm_fwd(const float* g, const float* v, int K, int d, void* w_bf16, float* w_f32, cudaStream_t s);
+int ssl_weightnorm_bwd(const float* g, const float* v, const float* dW, int64_t ld_dw, int K, int d, float* dg, float* dv,
+                       cudaStream_t s);
+int ssl_koleo_fwd(const float* xn, int groups, int n, int D, float eps, float w, int* nn, float* dist, float* row_loss,
+                  cudaStream_t s);
+int ssl_koleo_bwd(const float* x, const float* xn, int groups, int n, int D, float eps, float norm_eps, float w,
+                  const int* nn, const float* dist, const float* gscale, float* dx, cudaStream_t s);
+int ssl_ema(float* t, const float* sp, int64_t n, float m, cudaStream_t s);
+
 }  // namespace apla

@@ -149,6 +149,62 @@ int apla_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, int
 int apla_proj_refresh(const float* w1, const float* b1, const int32_t* idx, void* wfull, void* wfullT, float* bfull,
                       int L, int r, int D, int64_t w1_block_stride, int64_t b1_block_stride, apla_stream_t stream);
 
+/* --- DINOv2 self-supervised objective: HBM-bound row kernels (BASELINE config C4) ------- */
+/* Paths below are relative to src/self_supervised/dinov2/.  K = number of prototypes (65 536 in the shipped configs),
+ * K % 4 == 0, rows 16-byte aligned.  All tensors f32 unless a name says bf16.  Reductions are fixed-order.
+ * STATUS: built for sm_100a, first hardware run scheduled for round 2 (tests/test_ssl_gpu.py). */
+/* out[rows,K] = softmax((t - center[K]) * inv_temp): DINOLoss.softmax_center_teacher loss/dino_clstoken_loss.py:28-31,
+ * iBOTPatchLoss.softmax_center_teacher loss/ibot_patch_loss.py:39-51. */
+int apla_softmax_center(const float* t, int64_t ldt, const float* center, float inv_temp, int rows, int K, float* out,
+                        int64_t ldo, apla_stream_t stream);
+/* out[K] = scale * sum over rows of a[rows,K]; ws = workspace of splits*K floats: torch.sum(teacher_output, dim=0)
+ * loss/dino_clstoken_loss.py:84 (scale 1) and torch.sum(teacher_patch_tokens.mean(1), dim=0) loss/ibot_patch_loss.py:131
+ * (scale 1/n).  The data-parallel all-reduce of out sits between this and apla_center_ema. */
+int apla_colsum_f32(const float* a, int64_t ld, int rows, int K, float* ws, int splits, float scale, float* out,
+                    apla_stream_t stream);
+/* center = center * momentum + batch_sum * inv_count * (1 - momentum): apply_center_update
+ * loss/dino_clstoken_loss.py:88-98, loss/ibot_patch_loss.py:134-145 (inv_count = 1 / (len * world)). */
+int apla_center_ema(float* center, const float* batch_sum, int K, float inv_count, float momentum,
+                    apla_stream_t stream);
+/* Soft-target cross-entropy rows: q = t0[row % t_rows] (+ t1[row % t_rows] if t1 != NULL), z = s * inv_temp,
+ * row_loss[row] = -w (sum_k q_k z_k - mass lse(z)), w = w_uniform * (w_row ? w_row[row] : 1); lse / mass [rows] are
+ * kept for the backward.  One launch covers DINOLoss.forward over all crop pairs (loss/dino_clstoken_loss.py:62-74)
+ * or iBOTPatchLoss.forward_masked (loss/ibot_patch_loss.py:102-121). */
+int apla_soft_ce_fwd(const float* s, int64_t lds, int rows, int K, const float* t0, const float* t1, int64_t ldt,
+                     int t_rows, const float* w_row, float w_uniform, float inv_temp, float* row_loss, float* lse,
+                     float* mass, apla_stream_t stream);
+/* ds[rows,K] (f32, or bf16 if ds_is_bf16) = -w inv_temp *gscale (q - mass softmax(z)); gscale = device scalar with the
+ * upstream gradient (NULL = 1).  What autograd produces for the two losses above. */
+int apla_soft_ce_bwd(const float* s, int64_t lds, int rows, int K, const float* t0, const float* t1, int64_t ldt,
+                     int t_rows, const float* w_row, float w_uniform, float inv_temp, const float* lse,
+                     const float* mass, const float* gscale, void* ds, int64_t ldd, int ds_is_bf16,
+                     apla_stream_t stream);
+/* out[0] = scale * sum a[0..n) (single CTA, fixed order): the .mean() / .sum() that end the losses. */
+int apla_sum_f32(const float* a, int n, float scale, float* out, apla_stream_t stream);
+/* y = x / max(||x||, eps) per row of x[rows,d] (f32 or bf16), y as bf16 and / or f32 (either may be NULL):
+ * F.normalize in DINOHead.forward layers/dino_head.py:38-39; also the first line of KoLeoLoss loss/koleo_loss.py:41. */
+int apla_l2norm_fwd(const void* x, int64_t ldx, int x_is_f32, int rows, int d, float eps, void* y_bf16, float* y_f32,
+                    int64_t ldy, apla_stream_t stream);
+/* dx = (dy - y (y . dy)) / ||x||; dy and dx share one dtype (f32 or bf16). */
+int apla_l2norm_bwd(const void* x, int64_t ldx, int x_is_f32, const void* dy, int64_t ld_dy, int grads_are_f32,
+                    int rows, int d, float eps, void* dx, int64_t ld_dx, apla_stream_t stream);
+/* W[K,d] = g[K] v[K,d] / ||v[k,:]|| as bf16 and / or f32: weight_norm(nn.Linear(bottleneck, K, bias=False))
+ * layers/dino_head.py:27-31, and its backward from dW[K,d] (dg or dv may be NULL: weight_g is frozen when
+ * norm_last_layer is set). */
+int apla_weightnorm_fwd(const float* g, const float* v, int K, int d, void* w_bf16, float* w_f32,
+                        apla_stream_t stream);
+int apla_weightnorm_bwd(const float* g, const float* v, const float* dW, int64_t ld_dw, int K, int d, float* dg,
+                        float* dv, apla_stream_t stream);
+/* KoLeoLoss.forward loss/koleo_loss.py:23-45 on already L2-normalised rows xn[groups*n, D] (each group of n rows is
+ * one call of the reference): nn[i] = argmax_j!=i xn_i . xn_j, dist[i] = ||xn_i - xn_nn + 1e-8||,
+ * row_loss[i] = -w log(dist + eps) / n.  The backward returns the gradient for the UN-normalised rows x. */
+int apla_koleo_fwd(const float* xn, int groups, int n, int D, float eps, float w, int32_t* nn, float* dist,
+                   float* row_loss, apla_stream_t stream);
+int apla_koleo_bwd(const float* x, const float* xn, int groups, int n, int D, float eps, float norm_eps, float w,
+                   const int32_t* nn, const float* dist, const float* gscale, float* dx, apla_stream_t stream);
+/* teacher[n] = m teacher + (1 - m) student: DINOv2.update_teacher models.py:437-447. */
+int apla_ema_update(float* teacher, const float* student, int64_t n, float m, apla_stream_t stream);
+
 /* --- one block, two calls -------------------------------------------------------------------------------- */
 /* Block.forward (src/utils/transformers/vit.py:279-288: x += ls1(attn(norm1(x))); x += ls2(mlp(norm2(x)))) around an
  * APLA attention (src/apla/appla_attn.py:50-83) and its backward, as the launch sequences the step engine runs per

@@ -1,0 +1,171 @@
+"""Host logic of apla_b200/dinov2/loss.py on the CPU: the kernels of csrc/ssl.cu are replaced -- IN THIS TEST ONLY, by
+monkeypatching -- with torch restatements of what each C-ABI call computes (the closed forms of
+tests/test_ssl_closed_forms.py), and the GPU parity tests of tests/test_ssl_gpu.py are then run unchanged on the CPU.
+This pins everything around the kernels (crop-pair batching, the `chunk` view detection, row weights, the two-step centre
+protocol, autograd wiring, error paths) and keeps the GPU test file itself exercised while no GPU is at hand.  The
+product has no such fallback: without the patch every call below raises (test_no_fallback)."""
+import importlib.util
+import os
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class FakeOps:
+    """What the kernels compute, in torch, with the wrappers' signatures (apla_b200/dinov2/ops.py)."""
+    F32, BF16 = torch.float32, torch.bfloat16
+
+    @staticmethod
+    def _rows(t, name, dtype=torch.float32):
+        if t.dtype != dtype or t.dim() != 2 or t.stride(1) != 1:
+            raise RuntimeError(f"{name}: bad dtype / layout")
+        return t
+
+    @classmethod
+    def softmax_center(cls, t, center, temp, out=None):
+        cls._rows(t, "teacher_output")
+        if t.shape[1] % 4:
+            raise RuntimeError("K must be a multiple of 4")
+        return torch.softmax((t - center.reshape(1, -1)) * (1.0 / temp), dim=-1)
+
+    @classmethod
+    def colsum(cls, a, scale=1.0, splits=None):
+        return cls._rows(a, "a").sum(0, keepdim=True) * scale
+
+    @staticmethod
+    def center_ema_(center, batch_sum, count, momentum):
+        center.copy_(center * momentum + batch_sum.reshape(center.shape) * (1.0 / count) * (1 - momentum))
+        return center
+
+    @staticmethod
+    def _q(s, t0, t1, t_rows):
+        tr = torch.arange(s.shape[0]) % t_rows
+        return t0[tr] + (t1[tr] if t1 is not None else 0)
+
+    @classmethod
+    def soft_ce_fwd(cls, s, t0, t1, t_rows, w_row, w_uniform, inv_temp):
+        cls._rows(s, "s"); cls._rows(t0, "t0")
+        q = cls._q(s, t0, t1, t_rows)
+        z = s * inv_temp
+        lse, mass = torch.logsumexp(z, -1), q.sum(-1)
+        w = w_uniform * (w_row[:s.shape[0]] if w_row is not None else 1.0)
+        return (-w * ((q * z).sum(-1) - mass * lse)).sum(), lse, mass
+
+    @classmethod
+    def soft_ce_bwd(cls, s, t0, t1, t_rows, w_row, w_uniform, inv_temp, lse, mass, gscale, out_dtype=torch.float32):
+        q = cls._q(s, t0, t1, t_rows)
+        w = w_uniform * (w_row[:s.shape[0]] if w_row is not None else torch.ones(s.shape[0]))
+        c = -w * inv_temp * (gscale.reshape(()) if gscale is not None else 1.0)
+        return (c[:, None] * (q - mass[:, None] * torch.exp(s * inv_temp - lse[:, None]))).to(out_dtype)
+
+    @staticmethod
+    def l2norm_fwd(x, eps, out_dtype=torch.float32):
+        return torch.nn.functional.normalize(x.float(), dim=-1, eps=eps).to(out_dtype)
+
+    @staticmethod
+    def l2norm_bwd(x, dy, eps):
+        xf, g = x.float(), dy.float()
+        inv = 1 / xf.norm(dim=-1, keepdim=True).clamp(min=eps)
+        return (g * inv - xf * (xf * g).sum(-1, keepdim=True) * inv ** 3).to(dy.dtype)
+
+    @staticmethod
+    def weightnorm_fwd(g, v, out_dtype=torch.bfloat16):
+        return (v * (g.reshape(-1, 1) / v.norm(dim=1, keepdim=True))).to(out_dtype)
+
+    @staticmethod
+    def weightnorm_bwd(g, v, dW, need_dg=True, need_dv=True):
+        inv = 1 / v.norm(dim=1, keepdim=True)
+        vd = (v * dW).sum(1, keepdim=True)
+        dg = (vd * inv).reshape(g.shape) if need_dg else None
+        dv = g.reshape(-1, 1) * inv * (dW - v * vd * inv * inv) if need_dv else None
+        return dg, dv
+
+    @classmethod
+    def koleo_fwd(cls, x, eps, groups=1, weight=1.0):
+        n = x.shape[0] // groups
+        xn = cls.l2norm_fwd(x, eps)
+        nn_idx, dist = [], []
+        for g in range(groups):
+            b = xn[g * n:(g + 1) * n]
+            dots = (b @ b.t()).masked_fill(torch.eye(n, dtype=torch.bool), -1.0)
+            i = dots.argmax(1)
+            nn_idx.append(i.to(torch.int32)); dist.append((b - b[i] + 1e-8).norm(dim=-1))
+        nn_idx, dist = torch.cat(nn_idx), torch.cat(dist)
+        return (-torch.log(dist + eps) * weight / n).sum(), xn, nn_idx, dist
+
+    @staticmethod
+    def koleo_bwd(x, xn, nn_idx, dist, eps, gscale, groups=1, weight=1.0):
+        n = x.shape[0] // groups
+        up = -(weight / n) * (gscale.reshape(()) if gscale is not None else 1.0)
+        c = up / ((dist + eps) * dist)
+        gi = torch.zeros_like(xn)
+        for g in range(groups):
+            o = g * n
+            for i in range(n):
+                j = o + int(nn_idx[o + i])
+                u = xn[o + i] - xn[j] + 1e-8
+                gi[o + i] += c[o + i] * u
+                gi[j] -= c[o + i] * u
+        inv = 1 / x.norm(dim=-1, keepdim=True).clamp(min=eps)
+        return gi * inv - x * (x * gi).sum(-1, keepdim=True) * inv ** 3
+
+    @staticmethod
+    def ema_update_(teacher, student, m):
+        teacher.mul_(m).add_(student, alpha=1 - m)
+        return teacher
+
+
+def _load_gpu_tests():
+    spec = importlib.util.spec_from_file_location("_ssl_gpu_tests", os.path.join(HERE, "test_ssl_gpu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+G = _load_gpu_tests()
+CASES = []
+for _name in sorted(dir(G)):
+    _fn = getattr(G, _name)
+    if not _name.startswith("test_") or not callable(_fn):
+        continue
+    _params = [m for m in getattr(_fn, "pytestmark", []) if m.name == "parametrize"]
+    if not _params:
+        CASES.append(pytest.param(_name, {}, id=_name))
+        continue
+    _names = [a.strip() for a in _params[0].args[0].split(",")]
+    for _vals in _params[0].args[1]:
+        _vals = _vals if isinstance(_vals, (tuple, list)) else (_vals,)
+        _kw = dict(zip(_names, _vals))
+        if _kw.get("K", 0) >= 65536 or _kw.get("n", 0) >= 1 << 20:
+            _kw = {k: (4096 if k == "K" else v) for k, v in _kw.items()}   # keep the CPU run short
+            if _kw.get("n", 0) >= 1 << 20:
+                _kw["n"] = 1 << 14
+        CASES.append(pytest.param(_name, _kw, id=f"{_name}-{'-'.join(str(v) for v in _kw.values())}"))
+
+
+@pytest.mark.parametrize("name,kwargs", CASES)
+def test_gpu_suite_on_cpu_with_emulated_kernels(name, kwargs, monkeypatch):
+    import apla_b200.dinov2 as D
+    from apla_b200.dinov2 import loss
+    monkeypatch.setattr(loss, "ops", FakeOps)
+    monkeypatch.setattr(G, "DEV", "cpu")
+    monkeypatch.setattr(G, "_dinov2", lambda: (D, FakeOps))
+    getattr(G, name)(**kwargs)
+
+
+def test_no_fallback():
+    """Unpatched, the wrappers refuse to run without the device: nothing routes through torch math."""
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the CPU-only container")
+    import apla_b200.dinov2 as D
+    from apla_b200.dinov2 import ops
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        ops.softmax_center(torch.zeros(2, 64), torch.zeros(1, 64), 0.05)
+    with pytest.raises(RuntimeError):
+        D.DINOLoss(64)([torch.zeros(2, 64, requires_grad=True)], [torch.zeros(2, 64)])
+    with pytest.raises(RuntimeError):
+        D.KoLeoLoss()(torch.randn(4, 8))
+    with pytest.raises(RuntimeError):
+        D.update_teacher([torch.zeros(4)], [torch.zeros(4)], 0.99)
