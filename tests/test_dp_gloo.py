@@ -80,3 +80,56 @@ def test_two_rank_gradient_mean_equals_concatenated_batch(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     res = torch.load(out)
     assert res["err"] < 1e-5, res
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# centres of the self-supervised losses under data parallel ("C4 additionally all-reduces two 65 536-float
+# centres asynchronously"): host logic of apla_b200/dinov2/loss.py with the kernels emulated (tests/test_ssl_host.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def _centre_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ssl_host", os.path.join(os.path.dirname(__file__), "test_ssl_host.py"))
+    host = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(host)
+    from apla_b200.dinov2 import loss
+    loss.ops = host.FakeOps                                  # this process only
+    from oracle import ssl_oracle as S
+    K = 64
+    dl, il = loss.DINOLoss(K), loss.iBOTPatchLoss(K)
+    dc, ic = torch.zeros(1, K), torch.zeros(1, 1, K)
+    errs = []
+    for step in range(2):
+        g = torch.Generator().manual_seed(100 * step + rank)
+        n_masked = 5 + 3 * rank                              # ranks hold different numbers of masked patches
+        t_cls, t_patch = torch.randn(8, K, generator=g), torch.randn(1, n_masked, K, generator=g)
+        got_d = dl.softmax_center_teacher(t_cls, 0.05)
+        dl.update_center(t_cls)
+        got_i = il.softmax_center_teacher(t_patch, 0.05)
+        il.update_center(t_patch)
+        errs.append(float((got_d - S.softmax_center_teacher(t_cls, dc, 0.05)).abs().max()))
+        errs.append(float((got_i - S.softmax_center_teacher(t_patch, ic, 0.05)).abs().max()))
+        # what the reference computes: all-reduced row sum / (len * world) for DINO, mean over ranks of the per-rank
+        # patch means for iBOT (dino_clstoken_loss.py:76-98, ibot_patch_loss.py:123-145)
+        cls_all = [torch.zeros_like(t_cls) for _ in range(world)]
+        dist.all_gather(cls_all, t_cls)
+        means = [torch.zeros(1, K) for _ in range(world)]
+        dist.all_gather(means, t_patch.mean(1))
+        dc = dc * 0.9 + torch.cat(cls_all).mean(0, keepdim=True) * 0.1
+        ic = ic * 0.9 + (sum(means) / world).view(1, 1, K) * 0.1
+    dl.apply_center_update(); il.apply_center_update()
+    errs.append(float((dl.center - dc).abs().max()))
+    errs.append(float((il.center - ic).abs().max()))
+    if rank == 0:
+        torch.save({"errs": errs}, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_centre_updates(tmp_path):
+    out = str(tmp_path / "centres.pt")
+    mp.spawn(_centre_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out)
+    assert max(res["errs"]) < 1e-5, res

@@ -1,0 +1,14 @@
+#!/bin/bash
+# First GPU job of round 2: the self-supervised row kernels (csrc/ssl.cu) have never run on hardware.
+#   gpurun --timeout 900 -- 'bash tools/round2_first_gpu.sh'
+# 1. parity tests with the xfail marks off, 2. compute-sanitizer on the small cases, 3. per-kernel HBM fractions,
+# 4. launch list of the kernel bench.  Everything lands in gpurun_out/ssl_r2_*.
+set -u
+mkdir -p gpurun_out
+APLA_B200_SSL_STRICT=1 timeout 600 python -m pytest tests/test_ssl_gpu.py -q -m gpu -x 2>&1 | tail -40 > gpurun_out/ssl_r2_pytest.txt
+APLA_B200_SSL_STRICT=1 timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_ssl_gpu.py -q -m gpu \
+    -k "not 65536 and not 1048576" 2>&1 | tail -40 > gpurun_out/ssl_r2_memcheck.txt
+timeout 600 python tools/bench_ssl_kernels.py > gpurun_out/ssl_r2_kernels.jsonl 2> gpurun_out/ssl_r2_kernels.err
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 200 \
+    --csv --log-file gpurun_out/ssl_r2_launches.csv python tools/bench_ssl_kernels.py > /dev/null 2>&1
+tail -5 gpurun_out/ssl_r2_pytest.txt; tail -3 gpurun_out/ssl_r2_memcheck.txt; cat gpurun_out/ssl_r2_kernels.jsonl
