@@ -247,6 +247,44 @@ def test_objective_matches_oracle_assembly():
         assert rel(gg, rr) < 1e-3
 
 
+@pytest.mark.parametrize("n,in_dim,hidden,bott,K,nlayers,bias", [(70, 64, 128, 64, 256, 3, True), (33, 128, 128, 64, 512, 1, True),
+                                                              (200, 1024, 2048, 256, 4096, 3, True),
+                                                              (70, 64, 128, 64, 256, 2, False)])
+def test_dino_head(n, in_dim, hidden, bott, K, nlayers, bias):
+    """DINOHead as one autograd node against the oracle's fp32 head on the same weights.  bf16 GEMM operands: relative
+    error <= 1e-2 on the scores and cosine >= 0.999 / relative error <= 3e-2 on every gradient."""
+    D, ops = _dinov2()
+    torch.manual_seed(3)
+    head = D.DINOHead(in_dim, K, nlayers=nlayers, hidden_dim=hidden, bottleneck_dim=bott, mlp_bias=bias)
+    with torch.no_grad():                                           # trunc_normal(0.02) leaves the head nearly linear
+        for name, p in head.named_parameters():
+            if name.endswith("weight"):
+                p.mul_(4.0)
+            elif name.endswith("bias"):
+                p.normal_(0, 0.1)
+            elif name.endswith("weight_g"):
+                p.add_(0.1 * torch.randn_like(p))
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in head.state_dict().items()}
+    x = gen(n, in_dim, seed=60)
+    dy = gen(n, K, seed=61) * 0.01
+    xr = x.clone().requires_grad_(True)
+    ref = S.dino_head_forward(sd, xr)
+    ref.backward(dy)
+    head = head.to(DEV)
+    xd = x.to(DEV).requires_grad_(True)
+    out = head(xd)
+    out.backward(dy.to(DEV))
+    assert out.dtype == torch.float32 and rel(out, ref) < 1e-2
+    got = dict(head.named_parameters())
+    for k, v in sd.items():
+        gk = got[k].grad
+        assert gk is not None and gk.shape == v.shape, k
+        cos = float(torch.nn.functional.cosine_similarity(gk.detach().double().flatten().cpu(), v.grad.double().flatten(), dim=0))
+        assert cos > 0.999 and rel(gk, v.grad) < 3e-2, (k, cos, rel(gk, v.grad))
+    assert rel(xd.grad, xr.grad) < 3e-2
+    assert list(head.state_dict().keys()) == list(sd.keys())
+
+
 def test_rejects_what_it_cannot_run():
     D, ops = _dinov2()
     with pytest.raises(RuntimeError):
@@ -255,3 +293,7 @@ def test_rejects_what_it_cannot_run():
         ops.softmax_center(torch.randn(4, 66, device=DEV), torch.zeros(1, 66, device=DEV), 0.05)   # K % 4
     with pytest.raises(NotImplementedError):
         D.DINOLoss(64).sinkhorn_knopp_teacher(torch.zeros(2, 64), 0.05)
+    with pytest.raises(NotImplementedError):
+        D.DINOHead(64, 256, use_bn=True)
+    with pytest.raises(RuntimeError, match="multiples of 64"):
+        D.DINOHead(48, 256, hidden_dim=128, bottleneck_dim=64)(torch.zeros(2, 48, device=DEV))

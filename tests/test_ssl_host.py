@@ -117,6 +117,72 @@ class FakeOps:
         return teacher
 
 
+class FakeGemm:
+    """The GEMM wrappers of apla_b200/ops.py that DINOHead composes, restated in torch with the kernels' rounding points
+    (bf16 operands and outputs, fp32 accumulation)."""
+
+    @staticmethod
+    def _chk(*ts):
+        for t in ts:
+            if t.dtype != torch.bfloat16 or t.dim() != 2:
+                raise RuntimeError("bf16 2-D operands expected")
+
+    @classmethod
+    def gemm_bias(cls, a, w, bias=None, out=None):
+        cls._chk(a, w)
+        y = a.float() @ w.float().t()
+        return (y + bias if bias is not None else y).bfloat16()
+
+    @classmethod
+    def gemm_bias_gelu(cls, a, w, bias=None, h=None, g=None):
+        cls._chk(a, w)
+        y = a.float() @ w.float().t()
+        y = y + bias if bias is not None else y
+        return y.bfloat16(), torch.nn.functional.gelu(y).bfloat16()
+
+    @classmethod
+    def gemm_bias_ls_residual(cls, a, w, bias, gamma, resid, out=None):
+        cls._chk(a, w)
+        y = a.float() @ w.float().t()
+        if bias is not None:
+            y = y + bias
+        if gamma is not None:
+            y = y * gamma
+        out.copy_(resid + y)
+        return out
+
+    @staticmethod
+    def ls_cast(x, gamma=None, out=None):
+        assert x.dtype == torch.float32
+        return (x if gamma is None else x * gamma).bfloat16()
+
+    @classmethod
+    def proj_wgrad(cls, dysub, x, dw1, r, rowmap=None):
+        cls._chk(dysub, x)
+        assert dw1.dtype == torch.float32 and dw1.shape == (r, x.shape[1]) and rowmap is None
+        dw1 += dysub.float().t()[:r] @ x.float()
+        return dw1
+
+    @classmethod
+    def gemm_dgrad(cls, dy, wt, out=None):
+        cls._chk(dy, wt)
+        assert wt.shape[1] == dy.shape[1]
+        return (dy.float() @ wt.float().t()).bfloat16()
+
+    @classmethod
+    def gemm_dgrad_gelu_bwd(cls, dy, wt, h, out=None):
+        cls._chk(dy, wt, h)
+        hf = h.float().requires_grad_(True)
+        with torch.enable_grad():
+            torch.nn.functional.gelu(hf).sum().backward()
+        return ((dy.float() @ wt.float().t()) * hf.grad).bfloat16()
+
+    @staticmethod
+    def colsum(dy, db, n, rowmap=None):
+        db += dy.float().sum(0)[:n]
+        return db
+
+
 def _load_gpu_tests():
     spec = importlib.util.spec_from_file_location("_ssl_gpu_tests", os.path.join(HERE, "test_ssl_gpu.py"))
     mod = importlib.util.module_from_spec(spec)
@@ -148,8 +214,10 @@ for _name in sorted(dir(G)):
 @pytest.mark.parametrize("name,kwargs", CASES)
 def test_gpu_suite_on_cpu_with_emulated_kernels(name, kwargs, monkeypatch):
     import apla_b200.dinov2 as D
-    from apla_b200.dinov2 import loss
+    from apla_b200.dinov2 import dino_head, loss
     monkeypatch.setattr(loss, "ops", FakeOps)
+    monkeypatch.setattr(dino_head, "R", FakeOps)
+    monkeypatch.setattr(dino_head, "G", FakeGemm)
     monkeypatch.setattr(G, "DEV", "cpu")
     monkeypatch.setattr(G, "_dinov2", lambda: (D, FakeOps))
     getattr(G, name)(**kwargs)
@@ -169,3 +237,5 @@ def test_no_fallback():
         D.KoLeoLoss()(torch.randn(4, 8))
     with pytest.raises(RuntimeError):
         D.update_teacher([torch.zeros(4)], [torch.zeros(4)], 0.99)
+    with pytest.raises(RuntimeError):
+        D.DINOHead(64, 256, hidden_dim=128, bottleneck_dim=64)(torch.zeros(2, 64))
