@@ -30,7 +30,7 @@ sys.path.insert(0, HERE)
 import xformers_shim  # noqa: E402
 
 CFG = dict(embed_dim=64, depth=2, num_heads=1, patch=14, global_px=56, local_px=28, B=2, n_global=2, n_local=8,
-           partial_size=16, K=256, head_hidden=96, head_bottleneck=32, teacher_temp=0.05, koleo_w=0.1, dino_w=1.0,
+           partial_size=16, K=256, head_hidden=128, head_bottleneck=64, teacher_temp=0.05, koleo_w=0.1, dino_w=1.0,
            ibot_w=1.0, momentum=0.994)
 
 

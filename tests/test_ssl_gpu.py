@@ -285,6 +285,38 @@ def test_dino_head(n, in_dim, hidden, bott, K, nlayers, bias):
     assert list(head.state_dict().keys()) == list(sd.keys())
 
 
+def test_ssl_step_against_reference_vectors():
+    """Two whole self-supervised steps -- fused multi-crop student / teacher backbones (apla_b200.apla), DINOHead, the
+    three losses, teacher EMA, centre updates -- against the vectors recorded from the reference's unmodified DINOv2
+    meta-architecture (tests/golden/make_golden_ssl_step.py).  Bars: tests/helpers.py SSL_BF16_BARS."""
+    D, ops = _dinov2()
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import helpers
+    from apla_b200.config import AplaConfig
+    from apla_b200.hostdino import SSLMetaArch, build_dino_backbone
+    from apla_b200.hostvit import VitArch
+    cfg, student, teacher, trainable, batch, arr = helpers.ssl_step_case()
+    arch = VitArch(cfg["embed_dim"], cfg["depth"], cfg["num_heads"])
+
+    def make(sd):
+        inds = [sd[f"backbone.blocks.{i}.attn.inds"] for i in range(cfg["depth"])]
+        bb = build_dino_backbone(arch, img_size=cfg["global_px"], patch_size=cfg["patch"],
+                                 apla_config=AplaConfig(cfg["partial_size"]), indices=inds)
+        bb.load_state_dict({k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")}, strict=True)
+        head = D.DINOHead(cfg["embed_dim"], cfg["K"], nlayers=3, hidden_dim=cfg["head_hidden"],
+                          bottleneck_dim=cfg["head_bottleneck"])
+        head.load_state_dict({k[len("dino_head."):]: v for k, v in sd.items() if k.startswith("dino_head.")})
+        return bb, head
+
+    (sb, sh), (tb, th) = make(student), make(teacher)
+    model = SSLMetaArch(sb, tb, sh, th, cfg["K"], n_global_crops=cfg["n_global"], n_local_crops=cfg["n_local"],
+                        dino_loss_weight=cfg["dino_w"], koleo_loss_weight=cfg["koleo_w"],
+                        ibot_loss_weight=cfg["ibot_w"]).to(DEV)
+    assert sorted(n for n, p in model.student.named_parameters() if p.requires_grad) == sorted(trainable)
+    helpers.run_ssl_meta_steps(model, cfg, trainable, batch, arr)
+
+
 def test_rejects_what_it_cannot_run():
     D, ops = _dinov2()
     with pytest.raises(RuntimeError):

@@ -239,3 +239,119 @@ def test_no_fallback():
         D.update_teacher([torch.zeros(4)], [torch.zeros(4)], 0.99)
     with pytest.raises(RuntimeError):
         D.DINOHead(64, 256, hidden_dim=128, bottleneck_dim=64)(torch.zeros(2, 64))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the whole step: SSLMetaArch (apla_b200/hostdino.py) + DINOHead + the loss classes against the vectors recorded from the
+# reference's DINOv2 meta-architecture.  On the CPU the backbone is the oracle's (the APLA attention has no CPU path) and
+# the kernels under the head / losses are the emulations above; tests/test_ssl_gpu.py runs the same check with the fused
+# multi-crop backbone and the real kernels.
+# ---------------------------------------------------------------------------------------------------------------------
+class OracleDinoBackbone(torch.nn.Module):
+    """TEST-ONLY backbone: parameters registered under the reference's names, arithmetic by oracle/ssl_oracle.py."""
+
+    def __init__(self, sd, trainable, cfg):
+        super().__init__()
+        self.cfg = cfg
+        for k, v in sd.items():                                 # nested containers -> the reference's dotted names
+            *path, leaf = k.split(".")
+            mod = self
+            for part in path:
+                if not hasattr(mod, part):
+                    mod.add_module(part, torch.nn.Module())
+                mod = getattr(mod, part)
+            if v.is_floating_point():
+                mod.register_parameter(leaf, torch.nn.Parameter(v.clone(), requires_grad=k in trainable))
+            else:
+                mod.register_buffer(leaf, v.clone())
+
+    def forward(self, x, masks=None, is_training=True):
+        from oracle import ssl_oracle as S
+        sd = {"backbone." + k: v for k, v in list(self.named_parameters()) + list(self.named_buffers())}
+        kw = dict(patch=self.cfg["patch"], depth=self.cfg["depth"], num_heads=self.cfg["num_heads"])
+        if isinstance(x, (list, tuple)):
+            return [dict(x_norm_clstoken=o["cls"], x_norm_patchtokens=o["patch"]) for o in S.dinov2_backbone(sd, x, masks, **kw)]
+        o = S.dinov2_backbone(sd, x, masks, **kw)
+        return dict(x_norm_clstoken=o["cls"], x_norm_patchtokens=o["patch"])
+
+
+class ExactGemm(FakeGemm):
+    """The same wrappers with NO rounding (used with dino_head.BF16 patched to float32): isolates the wiring."""
+
+    @staticmethod
+    def _chk(*ts):
+        pass
+
+    @staticmethod
+    def gemm_bias(a, w, bias=None, out=None):
+        y = a @ w.t()
+        return y + bias if bias is not None else y
+
+    @staticmethod
+    def gemm_bias_gelu(a, w, bias=None, h=None, g=None):
+        y = a @ w.t()
+        y = y + bias if bias is not None else y
+        return y, torch.nn.functional.gelu(y)
+
+    @staticmethod
+    def ls_cast(x, gamma=None, out=None):
+        return x if gamma is None else x * gamma
+
+    @staticmethod
+    def gemm_dgrad(dy, wt, out=None):
+        return dy @ wt.t()
+
+    @staticmethod
+    def gemm_dgrad_gelu_bwd(dy, wt, h, out=None):
+        hf = h.clone().requires_grad_(True)
+        with torch.enable_grad():
+            torch.nn.functional.gelu(hf).sum().backward()
+        return (dy @ wt.t()) * hf.grad
+
+
+class ExactOps(FakeOps):
+    @staticmethod
+    def l2norm_fwd(x, eps, out_dtype=torch.float32):
+        return torch.nn.functional.normalize(x.float(), dim=-1, eps=eps)
+
+    @staticmethod
+    def weightnorm_fwd(g, v, out_dtype=torch.float32):
+        return v * (g.reshape(-1, 1) / v.norm(dim=1, keepdim=True))
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact-arithmetic", "bf16-rounding-points"])
+def test_meta_arch_two_steps_against_reference_vectors(monkeypatch, exact):
+    import sys
+    sys.path.insert(0, HERE)
+    import helpers
+    import apla_b200.dinov2 as D
+    from apla_b200.dinov2 import dino_head, loss
+    from apla_b200.hostdino import SSLMetaArch
+    monkeypatch.setattr(loss, "ops", FakeOps)
+    monkeypatch.setattr(dino_head, "R", ExactOps if exact else FakeOps)
+    monkeypatch.setattr(dino_head, "G", ExactGemm if exact else FakeGemm)
+    if exact:
+        monkeypatch.setattr(dino_head, "BF16", torch.float32)
+    cfg, student, teacher, trainable, batch, arr = helpers.ssl_step_case()
+
+    def split(sd):
+        bb = {k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")}
+        hd = {k[len("dino_head."):]: v for k, v in sd.items() if k.startswith("dino_head.")}
+        return bb, hd
+
+    def head_of(hd):
+        h = D.DINOHead(cfg["embed_dim"], cfg["K"], nlayers=3, hidden_dim=cfg["head_hidden"],
+                       bottleneck_dim=cfg["head_bottleneck"])
+        h.load_state_dict(hd)
+        return h
+
+    (sbb, shd), (tbb, thd) = split(student), split(teacher)
+    bb_train = {n[len("backbone."):] for n in trainable if n.startswith("backbone.")}
+    model = SSLMetaArch(OracleDinoBackbone(sbb, bb_train, cfg), OracleDinoBackbone(tbb, set(), cfg), head_of(shd),
+                        head_of(thd), cfg["K"], n_global_crops=cfg["n_global"], n_local_crops=cfg["n_local"],
+                        dino_loss_weight=cfg["dino_w"], koleo_loss_weight=cfg["koleo_w"], ibot_loss_weight=cfg["ibot_w"])
+    assert sorted(n for n, p in model.student.named_parameters() if p.requires_grad) == sorted(trainable)
+    assert not any(p.requires_grad for p in model.teacher.parameters())
+    ema = lambda s, t, m: [FakeOps.ema_update_(b.data, a.data, m) for a, b in zip(s, t)]      # noqa: E731
+    bars = ((1e-5, 0.999999, 1e-5),) * 2 if exact else helpers.SSL_BF16_BARS
+    helpers.run_ssl_meta_steps(model, cfg, trainable, batch, arr, ema_fn=ema, bars=bars)
