@@ -196,6 +196,8 @@ for _name in sorted(dir(G)):
     _fn = getattr(G, _name)
     if not _name.startswith("test_") or not callable(_fn):
         continue
+    if _name == "test_ssl_step_against_reference_vectors":      # needs the real fused backbone; its CPU counterpart is
+        continue                                                # test_meta_arch_two_steps_against_reference_vectors
     _params = [m for m in getattr(_fn, "pytestmark", []) if m.name == "parametrize"]
     if not _params:
         CASES.append(pytest.param(_name, {}, id=_name))
