@@ -12,3 +12,7 @@ timeout 600 python tools/bench_ssl_kernels.py > gpurun_out/ssl_r2_kernels.jsonl 
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 200 \
     --csv --log-file gpurun_out/ssl_r2_launches.csv python tools/bench_ssl_kernels.py > /dev/null 2>&1
 tail -5 gpurun_out/ssl_r2_pytest.txt; tail -3 gpurun_out/ssl_r2_memcheck.txt; cat gpurun_out/ssl_r2_kernels.jsonl
+# 5. the whole C4-shape step (module-level path), small first, then the real shape
+timeout 300 python tools/bench_ssl_step.py --arch vit_base --images 8 --K 4096 --steps 3 --warmup 2 > gpurun_out/ssl_r2_step_small.json 2> gpurun_out/ssl_r2_step_small.err
+timeout 600 python tools/bench_ssl_step.py --steps 3 --warmup 2 > gpurun_out/ssl_r2_step_c4.json 2> gpurun_out/ssl_r2_step_c4.err
+cat gpurun_out/ssl_r2_step_small.json gpurun_out/ssl_r2_step_c4.json; tail -3 gpurun_out/ssl_r2_step_c4.err
