@@ -357,3 +357,33 @@ def test_meta_arch_two_steps_against_reference_vectors(monkeypatch, exact):
     ema = lambda s, t, m: [FakeOps.ema_update_(b.data, a.data, m) for a, b in zip(s, t)]      # noqa: E731
     bars = ((1e-5, 0.999999, 1e-5),) * 2 if exact else helpers.SSL_BF16_BARS
     helpers.run_ssl_meta_steps(model, cfg, trainable, batch, arr, ema_fn=ema, bars=bars)
+
+
+def test_c_abi_argument_checks_without_a_gpu():
+    """Every self-supervised entry point refuses malformed sizes BEFORE touching the device: exercises the ctypes
+    marshalling of each signature (argument count, order and types as parsed from include/apla_b200.h) on the CPU."""
+    from apla_b200._lib import LIB
+    dll = LIB.load()
+    bad = {
+        "apla_softmax_center": (None, 0, None, 1.0, 1, 6, None, 0, None),                       # K % 4
+        "apla_colsum_f32": (None, 0, 1, 0, None, 1, 1.0, None, None),                           # K = 0
+        "apla_center_ema": (None, None, 0, 1.0, 0.9, None),                                     # K = 0
+        "apla_soft_ce_fwd": (None, 0, 1, 6, None, None, 0, 1, None, 1.0, 10.0, None, None, None, None),
+        "apla_soft_ce_bwd": (None, 0, 1, 8, None, None, 0, 0, None, 1.0, 10.0, None, None, None, None, 0, 0, None),
+        "apla_sum_f32": (None, -1, 1.0, None, None),
+        "apla_l2norm_fwd": (None, 0, 1, 1, 0, 1e-12, None, None, 0, None),                      # d = 0
+        "apla_l2norm_bwd": (None, 0, 1, None, 0, 1, 1, 0, 1e-12, None, 0, None),
+        "apla_weightnorm_fwd": (None, None, 0, 4, None, None, None),
+        "apla_weightnorm_bwd": (None, None, None, 0, 0, 4, None, None, None),
+        "apla_koleo_fwd": (None, 1, 1, 8, 1e-8, 1.0, None, None, None, None),                   # n < 2
+        "apla_koleo_bwd": (None, None, 1, 1, 8, 1e-8, 1e-8, 1.0, None, None, None, None, None),
+        "apla_ema_update": (None, None, -1, 0.99, None),
+    }
+    for name, args in bad.items():
+        assert len(args) == len(LIB.protos[name][1]), name
+        rc = getattr(dll, name)(*args)
+        assert rc == 1, (name, rc)
+        assert dll.apla_last_error(), name
+    # a wide row buffer is refused rather than launched with too much shared memory
+    assert dll.apla_koleo_fwd(None, 1, 4, 20000, 1e-8, 1.0, None, None, None, None) == 1
+    assert b"too wide" in dll.apla_last_error()
