@@ -11,8 +11,10 @@
 // (paths relative to src/self_supervised/dinov2/ of the reference).  All arithmetic is fp32; one CTA per K-wide row with
 // an online max / sum-of-exponentials pass and 128-bit loads, one warp per row for the narrow (bottleneck-wide) rows.
 // Reductions are fixed-order (no atomics): the losses are reproducible run to run.
-// STATUS: compiled for sm_100a; the GPU budget of round 1 was spent before these could be run on hardware -- the parity
-// tests (tests/test_ssl_gpu.py) are the first thing to run in round 2.
+// STATUS: compiled for sm_100a; round 1's GPU budget was spent before these existed, so their first HARDWARE run is round
+// 2's first job (tools/round2_first_gpu.sh).  Until then this source is executed, unchanged, by a CPU SIMT emulator
+// (tests/emu/, one OS thread per CUDA thread, real barriers and warp shuffles) against the same parity tests as on the GPU
+// (tests/test_ssl_emu.py): indexing, reductions and barrier placement are pinned; speed and fast-math rounding are not.
 #include <math.h>
 
 #include "common.cuh"

@@ -15,7 +15,7 @@ Differences from the reference, all deliberate:
     scores once for the forward (per-row log-sum-exp kept) and once for the backward;
   * Sinkhorn-Knopp centring is not provided (no shipped config selects it): the methods raise NotImplementedError.
 Tested against oracle/ssl_oracle.py (itself pinned to the reference) in tests/test_ssl_gpu.py.
-STATUS: not yet run on hardware (see csrc/ssl.cu)."""
+STATUS: not yet run on hardware; verified on the CPU-emulated kernels (see csrc/ssl.cu, tests/test_ssl_emu.py)."""
 from __future__ import annotations
 
 from typing import List, Optional, Sequence

@@ -3,7 +3,8 @@ self-supervised objective"; kernels in csrc/ssl.cu).  Same rules as apla_b200/op
 the stream, every wrapper validates and raises, nothing falls back to PyTorch math.
 
 STATUS: the kernels are built for sm_100a but have not run on hardware yet (round 1's GPU budget was spent before they
-were written); tests/test_ssl_gpu.py holds them to oracle/ssl_oracle.py and is the first GPU job of round 2."""
+were written); tests/test_ssl_gpu.py holds them to oracle/ssl_oracle.py and is the first GPU job of round 2.  Until then
+tests/test_ssl_emu.py runs the same tests on the kernel source executed by a CPU SIMT emulator."""
 from __future__ import annotations
 
 from typing import Optional, Tuple
