@@ -36,6 +36,32 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+GUARD, SENTINEL = 64, 12345.678
+
+
+class _Guarded:
+    """Output buffers with sentinel-filled guard bands on both sides: an out-of-bounds WRITE of a kernel is caught after
+    the call (the emulator itself would let it land in the heap silently)."""
+    live = []
+
+    @classmethod
+    def empty(cls, *shape, dtype=F32):
+        n = 1
+        for d in shape:
+            n *= d
+        flat = torch.full((n + 2 * GUARD,), SENTINEL).to(dtype)
+        cls.live.append(flat)
+        return flat[GUARD:GUARD + n].view(*shape) if shape else flat[GUARD:GUARD + 1].view(())
+
+    @classmethod
+    def check(cls, where):
+        for flat in cls.live:
+            want = torch.tensor(SENTINEL).to(flat.dtype)
+            assert bool((flat[:GUARD] == want).all()) and bool((flat[-GUARD:] == want).all()), \
+                f"{where} wrote outside its output buffer"
+        cls.live.clear()
+
+
 class EmuOps:
     """apla_b200/dinov2/ops.py's wrappers over the emulated library, for CPU tensors."""
     dll = None
@@ -45,6 +71,7 @@ class EmuOps:
         rc = getattr(cls.dll, name)(*args, None)
         if rc != 0:
             raise RuntimeError(f"{name} failed (rc={rc}): {cls.dll.emu_last_error().decode()}")
+        _Guarded.check(name)
 
     @staticmethod
     def _rows(t, name, dtype=F32):
@@ -56,7 +83,7 @@ class EmuOps:
     def softmax_center(cls, t, center, temp, out=None):
         cls._rows(t, "teacher_output")
         n, K = t.shape
-        out = torch.empty(n, K)
+        out = _Guarded.empty(n, K)
         cls.call("apla_softmax_center", _p(t), t.stride(0), _p(center), 1.0 / temp, n, K, _p(out), out.stride(0))
         return out
 
@@ -65,7 +92,7 @@ class EmuOps:
         cls._rows(a, "a")
         n, K = a.shape
         splits = splits or max(1, min(32, n // 64)) if n >= 64 else 3          # exercise ragged splits on small inputs
-        ws, out = torch.empty(splits, K), torch.empty(1, K)
+        ws, out = _Guarded.empty(splits, K), _Guarded.empty(1, K)
         cls.call("apla_colsum_f32", _p(a), a.stride(0), n, K, _p(ws), splits, float(scale), _p(out))
         return out
 
@@ -78,8 +105,8 @@ class EmuOps:
     def soft_ce_fwd(cls, s, t0, t1, t_rows, w_row, w_uniform, inv_temp):
         cls._rows(s, "s"); cls._rows(t0, "t0")
         rows, K = s.shape
-        row_loss = torch.empty(max(rows, 1)); lse = torch.empty_like(row_loss); mass = torch.empty_like(row_loss)
-        loss = torch.empty(())
+        row_loss, lse, mass = (_Guarded.empty(max(rows, 1)) for _ in range(3))
+        loss = _Guarded.empty()
         cls.call("apla_soft_ce_fwd", _p(s), s.stride(0), rows, K, _p(t0), _p(t1), t0.stride(0), int(t_rows), _p(w_row),
                  float(w_uniform), float(inv_temp), _p(row_loss), _p(lse), _p(mass))
         cls.call("apla_sum_f32", _p(row_loss), rows, 1.0, _p(loss))
@@ -88,7 +115,7 @@ class EmuOps:
     @classmethod
     def soft_ce_bwd(cls, s, t0, t1, t_rows, w_row, w_uniform, inv_temp, lse, mass, gscale, out_dtype=F32):
         rows, K = s.shape
-        ds = torch.empty(rows, K, dtype=out_dtype)
+        ds = _Guarded.empty(rows, K, dtype=out_dtype)
         cls.call("apla_soft_ce_bwd", _p(s), s.stride(0), rows, K, _p(t0), _p(t1), t0.stride(0), int(t_rows), _p(w_row),
                  float(w_uniform), float(inv_temp), _p(lse), _p(mass), _p(gscale), _p(ds), ds.stride(0),
                  int(out_dtype == BF16))
@@ -97,7 +124,7 @@ class EmuOps:
     @classmethod
     def l2norm_fwd(cls, x, eps, out_dtype=F32):
         n, d = x.shape
-        y = torch.empty(n, d, dtype=out_dtype)
+        y = _Guarded.empty(n, d, dtype=out_dtype)
         cls.call("apla_l2norm_fwd", _p(x), x.stride(0), int(x.dtype == F32), n, d, float(eps),
                  _p(y) if out_dtype == BF16 else None, _p(y) if out_dtype == F32 else None, y.stride(0))
         return y
@@ -105,7 +132,7 @@ class EmuOps:
     @classmethod
     def l2norm_bwd(cls, x, dy, eps):
         n, d = x.shape
-        dx = torch.empty(n, d, dtype=dy.dtype)
+        dx = _Guarded.empty(n, d, dtype=dy.dtype)
         cls.call("apla_l2norm_bwd", _p(x), x.stride(0), int(x.dtype == F32), _p(dy), dy.stride(0), int(dy.dtype == F32),
                  n, d, float(eps), _p(dx), dx.stride(0))
         return dx
@@ -113,7 +140,7 @@ class EmuOps:
     @classmethod
     def weightnorm_fwd(cls, g, v, out_dtype=BF16):
         K, d = v.shape
-        w = torch.empty(K, d, dtype=out_dtype)
+        w = _Guarded.empty(K, d, dtype=out_dtype)
         cls.call("apla_weightnorm_fwd", _p(g), _p(v), K, d, _p(w) if out_dtype == BF16 else None,
                  _p(w) if out_dtype == F32 else None)
         return w
@@ -121,8 +148,8 @@ class EmuOps:
     @classmethod
     def weightnorm_bwd(cls, g, v, dW, need_dg=True, need_dv=True):
         K, d = v.shape
-        dg = torch.empty_like(g) if need_dg else None
-        dv = torch.empty_like(v) if need_dv else None
+        dg = _Guarded.empty(*g.shape) if need_dg else None
+        dv = _Guarded.empty(*v.shape) if need_dv else None
         cls.call("apla_weightnorm_bwd", _p(g), _p(v), _p(dW), dW.stride(0), K, d, _p(dg), _p(dv))
         return dg, dv
 
@@ -130,8 +157,8 @@ class EmuOps:
     def koleo_fwd(cls, x, eps, groups=1, weight=1.0):
         n, D = x.shape[0] // groups, x.shape[1]
         xn = cls.l2norm_fwd(x, eps, F32)
-        nn = torch.empty(groups * n, dtype=I32); dist = torch.empty(groups * n); row_loss = torch.empty(groups * n)
-        loss = torch.empty(())
+        nn = _Guarded.empty(groups * n, dtype=I32); dist = _Guarded.empty(groups * n)
+        row_loss, loss = _Guarded.empty(groups * n), _Guarded.empty()
         cls.call("apla_koleo_fwd", _p(xn), groups, n, D, float(eps), float(weight), _p(nn), _p(dist), _p(row_loss))
         cls.call("apla_sum_f32", _p(row_loss), groups * n, 1.0, _p(loss))
         return loss, xn, nn, dist
@@ -139,7 +166,7 @@ class EmuOps:
     @classmethod
     def koleo_bwd(cls, x, xn, nn, dist, eps, gscale, groups=1, weight=1.0):
         n, D = x.shape[0] // groups, x.shape[1]
-        dx = torch.empty_like(x)
+        dx = _Guarded.empty(*x.shape)
         cls.call("apla_koleo_bwd", _p(x), _p(xn), groups, n, D, float(eps), float(eps), float(weight), _p(nn), _p(dist),
                  _p(gscale), _p(dx))
         return dx
