@@ -198,5 +198,15 @@ int apla_koleo_bwd(const float* x, const float* xn, int groups, int n, int D, fl
 int apla_ema_update(float* teacher, const float* student, int64_t n, float m, apla_stream_t stream) {
   return ssl_ema(teacher, student, n, m, S(stream));
 }
+int apla_ssl_objective(const float* s_scores, int64_t lds, const float* t_scores, int64_t ldt, float* t_probs, int64_t ldp,
+                       const float* dino_center, const float* ibot_center, const float* masks_weight, int B, int n_local,
+                       int n_masked, int K, float teacher_temp, float student_temp, float dino_weight, float ibot_weight,
+                       float* row_ws, float* col_ws, int splits, void* ds, int64_t ldd, int ds_is_bf16,
+                       const float* gscale, float* losses, float* dino_batch_sum, float* ibot_batch_mean,
+                       apla_stream_t stream) {
+  return ssl_objective(s_scores, lds, t_scores, ldt, t_probs, ldp, dino_center, ibot_center, masks_weight, B, n_local,
+                       n_masked, K, teacher_temp, student_temp, dino_weight, ibot_weight, row_ws, col_ws, splits, ds, ldd,
+                       ds_is_bf16, gscale, losses, dino_batch_sum, ibot_batch_mean, S(stream));
+}
 
 }  // extern "C"

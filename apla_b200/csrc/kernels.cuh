@@ -95,5 +95,10 @@ int ssl_koleo_fwd(const float* xn, int groups, int n, int D, float eps, float w,
 int ssl_koleo_bwd(const float* x, const float* xn, int groups, int n, int D, float eps, float norm_eps, float w,
                   const int* nn, const float* dist, const float* gscale, float* dx, cudaStream_t s);
 int ssl_ema(float* t, const float* sp, int64_t n, float m, cudaStream_t s);
+int ssl_objective(const float* s_scores, int64_t lds, const float* t_scores, int64_t ldt, float* t_probs, int64_t ldp,
+                  const float* dino_center, const float* ibot_center, const float* masks_weight, int B, int n_local,
+                  int n_masked, int K, float teacher_temp, float student_temp, float dino_weight, float ibot_weight,
+                  float* row_ws, float* col_ws, int splits, void* ds, int64_t ldd, int ds_is_bf16, const float* gscale,
+                  float* losses, float* dino_batch_sum, float* ibot_batch_mean, cudaStream_t s);
 
 }  // namespace apla

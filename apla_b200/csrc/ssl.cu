@@ -608,4 +608,62 @@ int ssl_ema(float* t, const float* sp, int64_t n, float m, cudaStream_t s) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// The objective of one self-supervised step on given head outputs, as ONE native launch sequence (no host code between
+// the launches): teacher targets for the CLS rows and the masked-patch rows, the two centre statistics, and forward +
+// backward of the three cross-entropy terms with the reference's scales (models.py:227-234, 374-433; two global crops).
+//   s_scores [n_local*B + 2B + n_masked, K]  student head output: local CLS rows (crop-major), global CLS rows, masked rows
+//   t_scores [2B + n_masked, K]              teacher head output: global CLS rows ALREADY swapped (models.py:244), masked rows
+//   t_probs  same shape, workspace           softmax((t - centre) / teacher_temp), kept for the backward
+//   row_ws   3 * student rows floats         per-row loss / log-sum-exp / target mass
+//   losses[3]                                dino_local_crops_loss, dino_global_crops_loss, 2 * ibot_loss  (loss_dict scale,
+//                                            i.e. before dino_weight / ibot_weight)
+//   ds                                       d(dino_weight (l + g) + ibot_weight i) / d s_scores, times *gscale
+//   dino_batch_sum[K], ibot_batch_mean[K]    inputs of apla_center_ema after the data-parallel all-reduce
+// ------------------------------------------------------------------------------------------------
+int ssl_objective(const float* s_scores, int64_t lds, const float* t_scores, int64_t ldt, float* t_probs, int64_t ldp,
+                  const float* dino_center, const float* ibot_center, const float* masks_weight, int B, int n_local,
+                  int n_masked, int K, float teacher_temp, float student_temp, float dino_weight, float ibot_weight,
+                  float* row_ws, float* col_ws, int splits, void* ds, int64_t ldd, int ds_is_bf16, const float* gscale,
+                  float* losses, float* dino_batch_sum, float* ibot_batch_mean, cudaStream_t s) {
+  APLA_CHECK(B > 0 && n_local >= 0 && n_masked >= 0 && K > 0, "ssl_objective: bad sizes B=%d n_local=%d n_masked=%d K=%d",
+             B, n_local, n_masked, K);
+  APLA_CHECK(teacher_temp > 0.f && student_temp > 0.f, "ssl_objective: temperatures must be positive");
+  const int n_g = 2 * B, n_l = n_local * B, rows = n_l + n_g + n_masked;
+  const float inv_tt = 1.f / teacher_temp, inv_st = 1.f / student_temp;
+  const int terms = 2 + (n_local * 2 > 1 ? n_local * 2 : 1);              // n_global_terms + n_local_terms
+  const size_t esz = ds_is_bf16 ? 2 : 4;
+  float *row_loss = row_ws, *lse = row_ws + rows, *mass = row_ws + 2 * size_t(rows);
+  // teacher: targets and centre statistics
+  if (int rc = ssl_softmax_center(t_scores, ldt, dino_center, inv_tt, n_g, K, t_probs, ldp, s)) return rc;
+  if (int rc = ssl_softmax_center(t_scores + n_g * ldt, ldt, ibot_center, inv_tt, n_masked, K, t_probs + n_g * ldp, ldp, s))
+    return rc;
+  if (int rc = ssl_colsum_f32(t_scores, ldt, n_g, K, col_ws, splits, 1.f, dino_batch_sum, s)) return rc;
+  if (int rc = ssl_colsum_f32(t_scores + n_g * ldt, ldt, n_masked, K, col_ws, splits,
+                              n_masked > 0 ? 1.f / n_masked : 0.f, ibot_batch_mean, s))
+    return rc;
+  // the three terms: {first student row, rows, t0, t1, t_rows, per-row weights, loss_dict scale, gradient weight}
+  struct Term { int r0, n; const float *t0, *t1; int t_rows; const float* w; float scale, weight; };
+  const Term term[3] = {
+      {0, n_l, t_probs, t_probs + int64_t(B) * ldp, B, nullptr, 1.f / (float(B) * terms), dino_weight},
+      {n_l, n_g, t_probs, nullptr, n_g, nullptr, 2.f / (float(n_g) * terms), dino_weight},
+      {n_l + n_g, n_masked, t_probs + int64_t(n_g) * ldp, nullptr, n_masked > 0 ? n_masked : 1, masks_weight,
+       1.f / float(n_g), ibot_weight}};                                    // 2 (loss_scales) * 1/2 (ibot_loss_scale) / 2B
+  for (int i = 0; i < 3; ++i) {
+    const Term& t = term[i];
+    const float* sp = s_scores + int64_t(t.r0) * lds;
+    if (int rc = ssl_soft_ce_fwd(sp, lds, t.n, K, t.t0, t.t1, ldp, t.t_rows, t.w, t.scale, inv_st, row_loss + t.r0,
+                                 lse + t.r0, mass + t.r0, s))
+      return rc;
+    if (int rc = ssl_sum_f32(row_loss + t.r0, t.n, 1.f, losses + i, s)) return rc;
+    if (ds != nullptr) {
+      void* dp = reinterpret_cast<char*>(ds) + size_t(t.r0) * size_t(ldd) * esz;
+      if (int rc = ssl_soft_ce_bwd(sp, lds, t.n, K, t.t0, t.t1, ldp, t.t_rows, t.w, t.scale * t.weight, inv_st, lse + t.r0,
+                                   mass + t.r0, gscale, dp, ldd, ds_is_bf16, s))
+        return rc;
+    }
+  }
+  return 0;
+}
+
 }  // namespace apla

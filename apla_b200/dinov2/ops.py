@@ -196,3 +196,39 @@ def ema_update_(teacher: torch.Tensor, student: torch.Tensor, m: float) -> torch
         raise RuntimeError("teacher and student differ in size")
     LIB.call("apla_ema_update", ptr(teacher), ptr(student), teacher.numel(), float(m), stream())
     return teacher
+
+
+def ssl_objective(s_scores: torch.Tensor, t_scores: torch.Tensor, dino_center: torch.Tensor, ibot_center: torch.Tensor,
+                  masks_weight: Optional[torch.Tensor], B: int, n_local: int, teacher_temp: float,
+                  student_temp: float = 0.1, dino_weight: float = 1.0, ibot_weight: float = 1.0,
+                  gscale: Optional[torch.Tensor] = None, ds_dtype=BF16, need_grad: bool = True):
+    """`apla_ssl_objective`: the whole objective of one step on given head outputs in one native launch sequence.
+    -> dict(losses [3] = dino_local, dino_global, 2 * ibot_loss; ds [rows, K] or None; t_probs; dino_batch_sum [1, K];
+    ibot_batch_mean [1, 1, K]).  Row layout of s_scores / t_scores: include/apla_b200.h."""
+    require_device()
+    s, t = _rows(s_scores, "s_scores"), _rows(t_scores, "t_scores")
+    rows, K = s.shape
+    n_masked = t.shape[0] - 2 * B
+    if n_masked < 0 or rows != n_local * B + 2 * B + n_masked or t.shape[1] != K:
+        raise RuntimeError(f"ssl_objective: {tuple(s.shape)} student rows / {tuple(t.shape)} teacher rows do not fit "
+                           f"B={B}, n_local={n_local}")
+    for c, name in ((dino_center, "dino_center"), (ibot_center, "ibot_center")):
+        if c.numel() != K or c.dtype != F32 or not c.is_contiguous() or not c.is_cuda:
+            raise RuntimeError(f"{name} must hold {K} contiguous f32 values on the device")
+    if n_masked > 0 and (masks_weight is None or masks_weight.numel() != n_masked or masks_weight.dtype != F32
+                         or not masks_weight.is_contiguous()):
+        raise RuntimeError("masks_weight must hold one contiguous f32 weight per masked patch")
+    dev = s.device
+    splits = max(1, min(32, max(2 * B, n_masked) // 64))
+    t_probs = torch.empty_like(t)
+    row_ws = torch.empty(3 * rows, device=dev, dtype=F32)
+    col_ws = torch.empty(splits, K, device=dev, dtype=F32)
+    losses = torch.empty(3, device=dev, dtype=F32)
+    dsum, imean = torch.empty(1, K, device=dev, dtype=F32), torch.empty(1, 1, K, device=dev, dtype=F32)
+    ds = torch.empty(rows, K, device=dev, dtype=ds_dtype) if need_grad else None
+    LIB.call("apla_ssl_objective", ptr(s), s.stride(0), ptr(t), t.stride(0), ptr(t_probs), t_probs.stride(0),
+             ptr(dino_center), ptr(ibot_center), ptr(masks_weight), B, n_local, n_masked, K, float(teacher_temp),
+             float(student_temp), float(dino_weight), float(ibot_weight), ptr(row_ws), ptr(col_ws), splits, ptr(ds),
+             K if ds is None else ds.stride(0), int(ds_dtype == BF16), ptr(gscale), ptr(losses), ptr(dsum), ptr(imean),
+             stream())
+    return dict(losses=losses, ds=ds, t_probs=t_probs, dino_batch_sum=dsum, ibot_batch_mean=imean)

@@ -204,6 +204,24 @@ int apla_koleo_bwd(const float* x, const float* xn, int groups, int n, int D, fl
                    const int32_t* nn, const float* dist, const float* gscale, float* dx, apla_stream_t stream);
 /* teacher[n] = m teacher + (1 - m) student: DINOv2.update_teacher models.py:437-447. */
 int apla_ema_update(float* teacher, const float* student, int64_t n, float m, apla_stream_t stream);
+/* The objective of one self-supervised step on given head outputs as ONE native launch sequence (13 launches, no host code
+ * between them): teacher targets + centre statistics + forward and backward of dino_local / dino_global / ibot with the
+ * scales of DINOv2.forward (models.py:227-234, 237-318, 374-433; two global crops, shared head, "centering").
+ *   s_scores [n_local*B + 2B + n_masked, K]: student head output = local CLS rows (crop-major), global CLS rows, masked rows;
+ *   t_scores [2B + n_masked, K]: teacher head output, global CLS rows already swapped (models.py:244), masked rows;
+ *   t_probs: workspace of t_scores' shape; row_ws: 3 * student-rows floats; col_ws: splits * K floats;
+ *   dino_center / ibot_center [K]: the centres to USE this step (pending update applied);
+ *   masks_weight [n_masked]: dinov2_utils.py:48;  ds (f32 or bf16, may be NULL): gradient of
+ *   dino_weight (local + global) + ibot_weight * ibot with respect to s_scores, times *gscale (NULL = 1);
+ *   losses[3] = dino_local_crops_loss, dino_global_crops_loss, 2 * ibot_loss as loss_dict reports them;
+ *   dino_batch_sum [K] / ibot_batch_mean [K]: all-reduce (sum) over the ranks, then apla_center_ema with
+ *   inv_count = 1 / (2B * world) and 1 / world respectively. */
+int apla_ssl_objective(const float* s_scores, int64_t lds, const float* t_scores, int64_t ldt, float* t_probs, int64_t ldp,
+                       const float* dino_center, const float* ibot_center, const float* masks_weight, int B, int n_local,
+                       int n_masked, int K, float teacher_temp, float student_temp, float dino_weight, float ibot_weight,
+                       float* row_ws, float* col_ws, int splits, void* ds, int64_t ldd, int ds_is_bf16,
+                       const float* gscale, float* losses, float* dino_batch_sum, float* ibot_batch_mean,
+                       apla_stream_t stream);
 
 /* --- one block, two calls -------------------------------------------------------------------------------- */
 /* Block.forward (src/utils/transformers/vit.py:279-288: x += ls1(attn(norm1(x))); x += ls2(mlp(norm2(x)))) around an

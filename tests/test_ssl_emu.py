@@ -176,6 +176,23 @@ class EmuOps:
         cls.call("apla_ema_update", _p(teacher), _p(student), teacher.numel(), float(m))
         return teacher
 
+    @classmethod
+    def ssl_objective(cls, s, t, dino_center, ibot_center, masks_weight, B, n_local, teacher_temp, student_temp=0.1,
+                      dino_weight=1.0, ibot_weight=1.0, gscale=None, ds_dtype=BF16, need_grad=True):
+        rows, K = s.shape
+        n_masked = t.shape[0] - 2 * B
+        splits = 3
+        t_probs, row_ws, col_ws = _Guarded.empty(*t.shape), _Guarded.empty(3 * rows), _Guarded.empty(splits, K)
+        losses, dsum, imean = _Guarded.empty(3), _Guarded.empty(1, K), _Guarded.empty(1, 1, K)
+        ds = _Guarded.empty(rows, K, dtype=ds_dtype) if need_grad else None
+        live = list(_Guarded.live)                      # the inner launchers are not wrapped: check once at the end
+        cls.call("apla_ssl_objective", _p(s), s.stride(0), _p(t), t.stride(0), _p(t_probs), t_probs.stride(0),
+                 _p(dino_center), _p(ibot_center), _p(masks_weight), B, n_local, n_masked, K, float(teacher_temp),
+                 float(student_temp), float(dino_weight), float(ibot_weight), _p(row_ws), _p(col_ws), splits, _p(ds),
+                 K if ds is None else ds.stride(0), int(ds_dtype == BF16), _p(gscale), _p(losses), _p(dsum), _p(imean))
+        del live
+        return dict(losses=losses, ds=ds, t_probs=t_probs, dino_batch_sum=dsum, ibot_batch_mean=imean)
+
 
 def _load(name):
     spec = importlib.util.spec_from_file_location("_" + name, os.path.join(HERE, name + ".py"))

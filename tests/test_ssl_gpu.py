@@ -285,6 +285,50 @@ def test_dino_head(n, in_dim, hidden, bott, K, nlayers, bias):
     assert list(head.state_dict().keys()) == list(sd.keys())
 
 
+@pytest.mark.parametrize("B,K,n_local,P,empty", [(3, 64, 4, 16, False), (4, 512, 8, 16, False), (2, 64, 0, 16, False),
+                                                 (3, 64, 2, 16, True)])
+def test_native_objective_sequence(B, K, n_local, P, empty):
+    """`apla_ssl_objective` (one native launch sequence) against the oracle's `ssl_objective` on given head outputs: the
+    three loss terms, the gradient with respect to every student score and both centre updates."""
+    D, ops = _dinov2()
+    g = torch.Generator().manual_seed(70)
+    masks = torch.zeros(2 * B, P, dtype=torch.bool) if empty else torch.rand(2 * B, P, generator=g) < 0.3
+    if not empty:
+        masks[0, 0] = True
+    mw = S.masks_weight_of(masks)
+    n = int(masks.sum())
+    s_all = gen(n_local * B + 2 * B + n, K, seed=71)
+    t_all = gen(2 * B + n, K, seed=72)
+    dc, ic = gen(1, K, seed=73, scale=0.2), gen(1, 1, K, seed=74, scale=0.2)
+    dino_w, ibot_w, temp = 0.8, 1.3, 0.05
+    # oracle: the same arithmetic as ssl_objective from the head outputs on (KoLeo acts on backbone features, not here)
+    a = s_all.clone().requires_grad_(True)
+    s_local, s_global, s_patch = a[:n_local * B], a[n_local * B:n_local * B + 2 * B], a[n_local * B + 2 * B:]
+    t_d = S.softmax_center_teacher(t_all[:2 * B], dc, temp).view(2, B, K)
+    t_i = S.softmax_center_teacher(t_all[2 * B:].unsqueeze(0), ic, temp).squeeze(0)
+    terms = 2 + max(2 * n_local, 1)
+    l = S.dino_loss(s_local.chunk(n_local), list(t_d)) / terms if n_local else torch.zeros(())
+    gl = S.dino_loss([s_global], [t_d.flatten(0, 1)]) * 2 / terms
+    ib = S.ibot_loss_masked(s_patch, t_i, masks, n_masked_patches=n, masks_weight=mw) * 2 * 0.5
+    (dino_w * (l + gl) + ibot_w * ib).backward()
+    up = torch.tensor(0.5)
+    res = ops.ssl_objective(s_all.to(DEV), t_all.to(DEV), dc.to(DEV), ic.to(DEV), mw.to(DEV), B, n_local, temp,
+                            dino_weight=dino_w, ibot_weight=ibot_w, gscale=up.to(DEV), ds_dtype=torch.float32)
+    want = torch.stack([l.detach(), gl.detach(), ib.detach()])
+    assert rel(res["losses"], want) < 1e-4, (res["losses"], want)
+    assert rel(res["ds"], a.grad * 0.5) < 1e-3
+    assert rel(res["t_probs"][:2 * B], t_d.flatten(0, 1)) < 1e-4
+    new_dc = dc.to(DEV).clone(); new_ic = ic.to(DEV).clone()
+    ops.center_ema_(new_dc, res["dino_batch_sum"], 2 * B, 0.9)
+    ops.center_ema_(new_ic, res["ibot_batch_mean"], 1, 0.9)
+    assert rel(new_dc, S.dino_center_update(dc, t_all[:2 * B], 0.9)) < 1e-5
+    if n:
+        assert rel(new_ic, S.ibot_center_update(ic, t_all[2 * B:].unsqueeze(0), 0.9)) < 1e-5
+    bf = ops.ssl_objective(s_all.to(DEV), t_all.to(DEV), dc.to(DEV), ic.to(DEV), mw.to(DEV), B, n_local, temp,
+                           dino_weight=dino_w, ibot_weight=ibot_w)
+    assert bf["ds"].dtype == torch.bfloat16 and rel(bf["ds"].float(), a.grad) < 6e-3
+
+
 def test_ssl_step_against_reference_vectors():
     """Two whole self-supervised steps -- fused multi-crop student / teacher backbones (apla_b200.apla), DINOHead, the
     three losses, teacher EMA, centre updates -- against the vectors recorded from the reference's unmodified DINOv2

@@ -116,6 +116,33 @@ class FakeOps:
         teacher.mul_(m).add_(student, alpha=1 - m)
         return teacher
 
+    @classmethod
+    def ssl_objective(cls, s, t, dino_center, ibot_center, masks_weight, B, n_local, teacher_temp, student_temp=0.1,
+                      dino_weight=1.0, ibot_weight=1.0, gscale=None, ds_dtype=torch.bfloat16, need_grad=True):
+        """The launch sequence of csrc/ssl.cu:ssl_objective, call for call."""
+        K = s.shape[1]
+        n_g, n_l = 2 * B, n_local * B
+        n_m = t.shape[0] - n_g
+        t_probs = torch.cat((cls.softmax_center(t[:n_g], dino_center, teacher_temp),
+                             cls.softmax_center(t[n_g:], ibot_center, teacher_temp) if n_m else t[n_g:]))
+        dsum = cls.colsum(t[:n_g])
+        imean = (cls.colsum(t[n_g:], 1.0 / n_m) if n_m else torch.zeros(1, K)).view(1, 1, K)
+        terms = 2 + max(2 * n_local, 1)
+        spec = [(0, n_l, t_probs[:B], t_probs[B:n_g], B, None, 1.0 / (B * terms), dino_weight),
+                (n_l, n_g, t_probs[:n_g], None, n_g, None, 2.0 / (n_g * terms), dino_weight),
+                (n_l + n_g, n_m, t_probs[n_g:], None, max(n_m, 1), masks_weight, 1.0 / n_g, ibot_weight)]
+        losses, ds = [], []
+        for r0, n, t0, t1, t_rows, w, scale, weight in spec:
+            sp = s[r0:r0 + n]
+            loss, lse, mass = cls.soft_ce_fwd(sp, t0, t1, t_rows, w, scale, 1.0 / student_temp) if n else \
+                (torch.zeros(()), None, None)
+            losses.append(loss)
+            if need_grad:
+                ds.append(cls.soft_ce_bwd(sp, t0, t1, t_rows, w, scale * weight, 1.0 / student_temp, lse, mass, gscale,
+                                          ds_dtype) if n else torch.zeros(0, K, dtype=ds_dtype))
+        return dict(losses=torch.stack(losses), ds=torch.cat(ds) if need_grad else None, t_probs=t_probs,
+                    dino_batch_sum=dsum, ibot_batch_mean=imean)
+
 
 class FakeGemm:
     """The GEMM wrappers of apla_b200/ops.py that DINOHead composes, restated in torch with the kernels' rounding points
@@ -378,6 +405,8 @@ def test_c_abi_argument_checks_without_a_gpu():
         "apla_koleo_fwd": (None, 1, 1, 8, 1e-8, 1.0, None, None, None, None),                   # n < 2
         "apla_koleo_bwd": (None, None, 1, 1, 8, 1e-8, 1e-8, 1.0, None, None, None, None, None),
         "apla_ema_update": (None, None, -1, 0.99, None),
+        "apla_ssl_objective": (None, 0, None, 0, None, 0, None, None, None, 0, 8, 0, 64, 0.05, 0.1, 1.0, 1.0, None, None, 1,
+                               None, 0, 1, None, None, None, None, None),                         # B = 0
     }
     for name, args in bad.items():
         assert len(args) == len(LIB.protos[name][1]), name
