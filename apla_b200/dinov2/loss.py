@@ -116,6 +116,16 @@ class DINOLoss(nn.Module):
             self.reduce_handle = dist.all_reduce(self.async_batch_center, async_op=True)
 
     @torch.no_grad()
+    def register_center_stat(self, batch_sum, n_rows):
+        """`reduce_center_update` for a statistic that is already computed (`apla_ssl_objective` returns the column sums of
+        the teacher's CLS scores): same pending-update protocol, same asynchronous all-reduce."""
+        self.updated = False
+        self.len_teacher_output = n_rows
+        self.async_batch_center = batch_sum.view(1, -1)
+        if dist.is_initialized():
+            self.reduce_handle = dist.all_reduce(self.async_batch_center, async_op=True)
+
+    @torch.no_grad()
     def apply_center_update(self):
         if self.updated is False:
             world_size = dist.get_world_size() if dist.is_initialized() else 1
@@ -181,6 +191,15 @@ class iBOTPatchLoss(nn.Module):
         b, n, K = teacher_patch_tokens.shape
         self.len_teacher_patch_tokens = b
         self.async_batch_center = ops.colsum(teacher_patch_tokens.reshape(b * n, K), 1.0 / max(n, 1)).view(1, 1, K)
+        if dist.is_initialized():
+            self.reduce_handle = dist.all_reduce(self.async_batch_center, async_op=True)
+
+    @torch.no_grad()
+    def register_center_stat(self, batch_mean, n_items=1):
+        """`reduce_center_update` for an already computed statistic (`apla_ssl_objective`'s mean over the masked rows)."""
+        self.updated = False
+        self.len_teacher_patch_tokens = n_items
+        self.async_batch_center = batch_mean.view(1, 1, -1)
         if dist.is_initialized():
             self.reduce_handle = dist.all_reduce(self.async_batch_center, async_op=True)
 

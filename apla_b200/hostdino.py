@@ -131,7 +131,7 @@ class SSLMetaArch(nn.Module):
     def __init__(self, student_backbone: nn.Module, teacher_backbone: nn.Module, student_head: nn.Module,
                  teacher_head: nn.Module, out_dim: int, *, n_global_crops: int = 2, n_local_crops: int = 8,
                  dino_loss_weight: float = 1.0, koleo_loss_weight: float = 0.1, ibot_loss_weight: float = 1.0,
-                 loss_classes=None):
+                 loss_classes=None, fused_objective: bool = False):
         super().__init__()
         if n_global_crops != 2:
             raise AssertionError("the objective is written for two global crops (models.py:214)")
@@ -148,6 +148,9 @@ class SSLMetaArch(nn.Module):
         self.n_global_crops, self.n_local_crops = n_global_crops, n_local_crops
         self.dino_loss_weight, self.koleo_loss_weight = dino_loss_weight, koleo_loss_weight
         self.ibot_loss_weight = ibot_loss_weight
+        # True: student head + the three cross-entropy terms as ONE autograd node over `apla_ssl_objective`
+        # (DINOHead.forward_with_objective); False: the reference's call structure, one loss-class call per term
+        self.fused_objective = fused_objective
 
     def forward(self, images: Dict[str, torch.Tensor], teacher_temp: float):
         dev = next(self.student.parameters()).device
@@ -171,6 +174,9 @@ class SSLMetaArch(nn.Module):
             t_patch = t["x_norm_patchtokens"].flatten(0, 1).index_select(0, mask_indices)
             t_out = self.teacher["dino_head"](torch.cat((t_cls, t_patch)))
             t_cls_out, t_patch_out = t_out[:n_cls], t_out[n_cls:n_cls + n_masked]
+        if self.fused_objective:
+            return self._forward_fused(t_out, global_crops, local_crops, masks, mask_indices, masks_weight, teacher_temp)
+        with torch.no_grad():
             t_dino = self.dino_loss.softmax_center_teacher(t_cls_out, teacher_temp=teacher_temp) \
                 .view(ng, -1, t_cls_out.shape[-1])
             self.dino_loss.update_center(t_cls_out)
@@ -203,6 +209,32 @@ class SSLMetaArch(nn.Module):
                                                 masks_weight=masks_weight) * loss_scales * ibot_loss_scale   # :423-433
         loss_dict["ibot_loss"] = i / 2
         total = total + self.ibot_loss_weight * i
+        return total, loss_dict
+
+    def _forward_fused(self, t_out, global_crops, local_crops, masks, mask_indices, masks_weight, teacher_temp):
+        ng, nl = self.n_global_crops, self.n_local_crops
+        with torch.no_grad():                       # the centres to use now = the ones updated with the previous batch
+            self.dino_loss.apply_center_update()
+            self.ibot_patch_loss.apply_center_update()
+        s_glob, s_loc = self.student["backbone"]([global_crops, local_crops], masks=[masks, None], is_training=True)
+        s_patch = s_glob["x_norm_patchtokens"].flatten(0, 1).index_select(0, mask_indices)
+        rows = torch.cat((s_loc["x_norm_clstoken"], s_glob["x_norm_clstoken"], s_patch))
+        B = s_glob["x_norm_clstoken"].shape[0] // ng
+        ce, losses, dsum, imean = self.student["dino_head"].forward_with_objective(
+            rows, t_scores=t_out, dino_center=self.dino_loss.center, ibot_center=self.ibot_patch_loss.center,
+            masks_weight=masks_weight.float().contiguous(), B=B, n_local=nl, teacher_temp=teacher_temp,
+            student_temp=self.dino_loss.student_temp, dino_weight=self.dino_loss_weight,
+            ibot_weight=self.ibot_loss_weight)
+        self.dino_loss.register_center_stat(dsum, ng * B)
+        self.ibot_patch_loss.register_center_stat(imean, 1)
+        loss_dict = {"dino_global_crops_loss": losses[1], "ibot_loss": losses[2] / 2}
+        if nl > 0:
+            loss_dict["dino_local_crops_loss"] = losses[0]
+        total = ce
+        if self.koleo_loss_weight > 0:
+            k = self.koleo_loss_weight * sum(self.koleo_loss(p) for p in s_glob["x_norm_clstoken"].chunk(2))
+            loss_dict["koleo_loss"] = k / 2
+            total = total + k
         return total, loss_dict
 
     @torch.no_grad()

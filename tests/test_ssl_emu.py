@@ -232,7 +232,8 @@ def test_gpu_suite_on_the_emulated_kernels(name, kwargs, emu, monkeypatch):
     getattr(G, name)(**kwargs)
 
 
-def test_meta_arch_step_on_the_emulated_kernels(emu, monkeypatch):
+@pytest.mark.parametrize("fused", [False, True], ids=["per-term-losses", "fused-head-objective"])
+def test_meta_arch_step_on_the_emulated_kernels(emu, monkeypatch, fused):
     """Two whole steps against the reference's recorded vectors with every ssl.cu kernel emulated (oracle backbone,
     GEMMs restated at their bf16 rounding points)."""
     EmuOps.dll = emu
@@ -256,6 +257,7 @@ def test_meta_arch_step_on_the_emulated_kernels(emu, monkeypatch):
     model = SSLMetaArch(HOST.OracleDinoBackbone(split(student, "backbone."), bb_train, cfg),
                         HOST.OracleDinoBackbone(split(teacher, "backbone."), set(), cfg), head_of(student),
                         head_of(teacher), cfg["K"], n_global_crops=cfg["n_global"], n_local_crops=cfg["n_local"],
-                        dino_loss_weight=cfg["dino_w"], koleo_loss_weight=cfg["koleo_w"], ibot_loss_weight=cfg["ibot_w"])
+                        dino_loss_weight=cfg["dino_w"], koleo_loss_weight=cfg["koleo_w"], ibot_loss_weight=cfg["ibot_w"],
+                        fused_objective=fused)
     ema = lambda s, t, m: [EmuOps.ema_update_(b.data, a.data, m) for a, b in zip(s, t)]            # noqa: E731
     helpers.run_ssl_meta_steps(model, cfg, trainable, batch, arr, ema_fn=ema)

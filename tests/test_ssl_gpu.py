@@ -329,7 +329,8 @@ def test_native_objective_sequence(B, K, n_local, P, empty):
     assert bf["ds"].dtype == torch.bfloat16 and rel(bf["ds"].float(), a.grad) < 6e-3
 
 
-def test_ssl_step_against_reference_vectors():
+@pytest.mark.parametrize("fused", [False, True], ids=["per-term-losses", "fused-head-objective"])
+def test_ssl_step_against_reference_vectors(fused):
     """Two whole self-supervised steps -- fused multi-crop student / teacher backbones (apla_b200.apla), DINOHead, the
     three losses, teacher EMA, centre updates -- against the vectors recorded from the reference's unmodified DINOv2
     meta-architecture (tests/golden/make_golden_ssl_step.py).  Bars: tests/helpers.py SSL_BF16_BARS."""
@@ -356,7 +357,7 @@ def test_ssl_step_against_reference_vectors():
     (sb, sh), (tb, th) = make(student), make(teacher)
     model = SSLMetaArch(sb, tb, sh, th, cfg["K"], n_global_crops=cfg["n_global"], n_local_crops=cfg["n_local"],
                         dino_loss_weight=cfg["dino_w"], koleo_loss_weight=cfg["koleo_w"],
-                        ibot_loss_weight=cfg["ibot_w"]).to(DEV)
+                        ibot_loss_weight=cfg["ibot_w"], fused_objective=fused).to(DEV)
     assert sorted(n for n, p in model.student.named_parameters() if p.requires_grad) == sorted(trainable)
     helpers.run_ssl_meta_steps(model, cfg, trainable, batch, arr)
 

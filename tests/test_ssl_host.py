@@ -348,8 +348,9 @@ class ExactOps(FakeOps):
         return v * (g.reshape(-1, 1) / v.norm(dim=1, keepdim=True))
 
 
+@pytest.mark.parametrize("fused", [False, True], ids=["per-term-losses", "fused-head-objective"])
 @pytest.mark.parametrize("exact", [True, False], ids=["exact-arithmetic", "bf16-rounding-points"])
-def test_meta_arch_two_steps_against_reference_vectors(monkeypatch, exact):
+def test_meta_arch_two_steps_against_reference_vectors(monkeypatch, exact, fused):
     import sys
     sys.path.insert(0, HERE)
     import helpers
@@ -378,7 +379,8 @@ def test_meta_arch_two_steps_against_reference_vectors(monkeypatch, exact):
     bb_train = {n[len("backbone."):] for n in trainable if n.startswith("backbone.")}
     model = SSLMetaArch(OracleDinoBackbone(sbb, bb_train, cfg), OracleDinoBackbone(tbb, set(), cfg), head_of(shd),
                         head_of(thd), cfg["K"], n_global_crops=cfg["n_global"], n_local_crops=cfg["n_local"],
-                        dino_loss_weight=cfg["dino_w"], koleo_loss_weight=cfg["koleo_w"], ibot_loss_weight=cfg["ibot_w"])
+                        dino_loss_weight=cfg["dino_w"], koleo_loss_weight=cfg["koleo_w"], ibot_loss_weight=cfg["ibot_w"],
+                        fused_objective=fused)
     assert sorted(n for n, p in model.student.named_parameters() if p.requires_grad) == sorted(trainable)
     assert not any(p.requires_grad for p in model.teacher.parameters())
     ema = lambda s, t, m: [FakeOps.ema_update_(b.data, a.data, m) for a, b in zip(s, t)]      # noqa: E731

@@ -44,7 +44,7 @@ def make_batch(B, n_local, global_px, local_px, patch, mask_prob=0.5, ratio=(0.1
             "n_masked_patches": torch.full((1,), idx.shape[0], dtype=torch.long)}
 
 
-def build(arch, K, partial_size, global_px, patch, hidden, bottleneck, n_local, device):
+def build(arch, K, partial_size, global_px, patch, hidden, bottleneck, n_local, device, fused_objective=True):
     from apla_b200.dinov2 import DINOHead
     torch.manual_seed(0)
     with contextlib.redirect_stdout(io.StringIO()):
@@ -58,7 +58,7 @@ def build(arch, K, partial_size, global_px, patch, hidden, bottleneck, n_local, 
     sh = DINOHead(D, K, nlayers=3, hidden_dim=hidden, bottleneck_dim=bottleneck)
     th = DINOHead(D, K, nlayers=3, hidden_dim=hidden, bottleneck_dim=bottleneck)
     th.load_state_dict(sh.state_dict())
-    return SSLMetaArch(student, teacher, sh, th, K, n_local_crops=n_local).to(device)
+    return SSLMetaArch(student, teacher, sh, th, K, n_local_crops=n_local, fused_objective=fused_objective).to(device)
 
 
 def main():
@@ -73,8 +73,12 @@ def main():
     ap.add_argument("--global-px", type=int, default=224)
     ap.add_argument("--local-px", type=int, default=98)
     ap.add_argument("--device", default="cuda")
+    ap.add_argument("--per-term-losses", action="store_true",
+                    help="the reference's call structure (one loss-class call per term) instead of the fused "
+                         "head + objective node")
     a = ap.parse_args()
-    model = build(a.arch, a.K, a.partial_size, a.global_px, 14, 2048, 256, a.n_local, a.device)
+    model = build(a.arch, a.K, a.partial_size, a.global_px, 14, 2048, 256, a.n_local, a.device,
+                  fused_objective=not a.per_term_losses)
     trainable = [p for p in model.student.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(trainable, lr=3e-5, weight_decay=1e-5)
     batch = make_batch(a.images, a.n_local, a.global_px, a.local_px, 14)
@@ -102,6 +106,7 @@ def main():
     full = a.arch == "vit_large" and a.K == 65536 and a.global_px == 224 and a.local_px == 98 and a.n_local == 8
     out = dict(workload=f"C4-shape SSL step: {a.arch}/14 student+teacher, {a.images} images -> {2 * a.images} x "
                         f"{a.global_px}px + {a.n_local * a.images} x {a.local_px}px crops, K={a.K}, r={a.partial_size}",
+               objective="per-term loss classes" if a.per_term_losses else "fused head + apla_ssl_objective",
                ms_per_step=round(ms, 2), images_per_s=round(a.images / ms * 1e3, 1), loss=float(loss),
                masked_patches=int(batch["mask_indices_list"].shape[0]), trainable_params=sum(p.numel() for p in trainable),
                tflops=round(GFLOP_PER_IMAGE_C4 * a.images / ms, 1) if full else None,

@@ -15,4 +15,5 @@ tail -5 gpurun_out/ssl_r2_pytest.txt; tail -3 gpurun_out/ssl_r2_memcheck.txt; ca
 # 5. the whole C4-shape step (module-level path), small first, then the real shape
 timeout 300 python tools/bench_ssl_step.py --arch vit_base --images 8 --K 4096 --steps 3 --warmup 2 > gpurun_out/ssl_r2_step_small.json 2> gpurun_out/ssl_r2_step_small.err
 timeout 600 python tools/bench_ssl_step.py --steps 3 --warmup 2 > gpurun_out/ssl_r2_step_c4.json 2> gpurun_out/ssl_r2_step_c4.err
-cat gpurun_out/ssl_r2_step_small.json gpurun_out/ssl_r2_step_c4.json; tail -3 gpurun_out/ssl_r2_step_c4.err
+timeout 600 python tools/bench_ssl_step.py --steps 3 --warmup 2 --per-term-losses > gpurun_out/ssl_r2_step_c4_perterm.json 2> gpurun_out/ssl_r2_step_c4_perterm.err
+cat gpurun_out/ssl_r2_step_small.json gpurun_out/ssl_r2_step_c4.json gpurun_out/ssl_r2_step_c4_perterm.json; tail -3 gpurun_out/ssl_r2_step_c4.err
