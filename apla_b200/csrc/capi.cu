@@ -168,6 +168,12 @@ int apla_soft_ce_bwd(const float* s, int64_t lds, int rows, int K, const float* 
   return ssl_soft_ce_bwd(s, lds, rows, K, t0, t1, ldt, t_rows, w_row, w_uniform, inv_temp, lse, mass, gscale, ds, ldd,
                          ds_is_bf16, S(stream));
 }
+int apla_soft_ce_fwd_bwd(const float* s, int64_t lds, int rows, int K, const float* t0, const float* t1, int64_t ldt,
+                         int t_rows, const float* w_row, float w_fwd, float w_bwd, float inv_temp, const float* gscale,
+                         float* row_loss, void* ds, int64_t ldd, int ds_is_bf16, apla_stream_t stream) {
+  return ssl_soft_ce_fwd_bwd(s, lds, rows, K, t0, t1, ldt, t_rows, w_row, w_fwd, w_bwd, inv_temp, gscale, row_loss, ds, ldd,
+                             ds_is_bf16, S(stream));
+}
 int apla_sum_f32(const float* a, int n, float scale, float* out, apla_stream_t stream) {
   return ssl_sum_f32(a, n, scale, out, S(stream));
 }

@@ -16,6 +16,7 @@
 // (tests/emu/, one OS thread per CUDA thread, real barriers and warp shuffles) against the same parity tests as on the GPU
 // (tests/test_ssl_emu.py): indexing, reductions and barrier placement are pinned; speed and fast-math rounding are not.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -218,6 +219,74 @@ soft_ce_bwd_kernel(const float* __restrict__ s, int64_t lds, int K, const float*
     g.y = c * (q.y - mass * __expf(a.y * inv_temp - lse));
     g.z = c * (q.z - mass * __expf(a.z * inv_temp - lse));
     g.w = c * (q.w - mass * __expf(a.w * inv_temp - lse));
+    if constexpr (sizeof(OutT) == 4) {
+      reinterpret_cast<float4*>(drow)[i] = g;
+    } else {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(g.x, g.y), hi = __floats2bfloat162_rn(g.z, g.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(drow)[i] = pk;
+    }
+  }
+}
+
+// forward and backward of one row in ONE launch (used when the upstream gradient is known when the loss is taken, i.e. by
+// ssl_objective): pass 1 = soft_ce_fwd_kernel, pass 2 = soft_ce_bwd_kernel walking the row BACKWARDS so that it starts
+// on the float4s this thread touched last -- the second read of the student / teacher rows is meant to come from L2
+// (0.5-0.75 MB per resident CTA), which makes the HBM traffic of the pair read-once + one write of ds.
+// w_fwd scales the reported row loss, w_bwd the gradient (loss_dict scale vs. scale x loss weight).
+template <typename OutT>
+__global__ void __launch_bounds__(kRowThreads)
+soft_ce_fused_kernel(const float* __restrict__ s, int64_t lds, int K, const float* __restrict__ t0,
+                     const float* __restrict__ t1, int64_t ldt, int t_rows, const float* __restrict__ w_row, float w_fwd,
+                     float w_bwd, float inv_temp, const float* __restrict__ gscale, float* __restrict__ row_loss,
+                     OutT* __restrict__ ds, int64_t ldd) {
+  __shared__ float red[33];
+  const int row = blockIdx.x;
+  const int trow = row % t_rows;
+  const float4* sr = reinterpret_cast<const float4*>(s + int64_t(row) * lds);
+  const float4* q0 = reinterpret_cast<const float4*>(t0 + int64_t(trow) * ldt);
+  const float4* q1 = t1 ? reinterpret_cast<const float4*>(t1 + int64_t(trow) * ldt) : nullptr;
+  const int nv = K >> 2;
+  float m = -INFINITY, l = 0.f, dot = 0.f, mass = 0.f;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    float4 a = sr[i];
+    float4 q = q0[i];
+    if (q1) {
+      const float4 b = q1[i];
+      q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w;
+    }
+    a.x *= inv_temp; a.y *= inv_temp; a.z *= inv_temp; a.w *= inv_temp;
+    const float cm = max4(a);
+    if (cm > m) { l *= __expf(m - cm); m = cm; }
+    l += (__expf(a.x - m) + __expf(a.y - m)) + (__expf(a.z - m) + __expf(a.w - m));
+    dot += (q.x * a.x + q.y * a.y) + (q.z * a.z + q.w * a.w);
+    mass += (q.x + q.y) + (q.z + q.w);
+  }
+  const float M = block_max(m, red);
+  const float L = block_sum(l > 0.f ? l * __expf(m - M) : 0.f, red);
+  const float DOT = block_sum(dot, red);
+  const float MASS = block_sum(mass, red);
+  const float lse = M + logf(L);
+  const float wr = w_row ? w_row[row] : 1.f;
+  if (threadIdx.x == 0) row_loss[row] = -w_fwd * wr * (DOT - MASS * lse);
+  const float c = -w_bwd * wr * inv_temp * (gscale ? gscale[0] : 1.f);
+  OutT* drow = ds + int64_t(row) * ldd;
+  const int tid = threadIdx.x, bd = blockDim.x;
+  const int last = tid < nv ? tid + ((nv - 1 - tid) / bd) * bd : -1;   // the last i of this thread's first pass
+  for (int i = last; i >= 0; i -= bd) {
+    const float4 a = sr[i];
+    float4 q = q0[i];
+    if (q1) {
+      const float4 b = q1[i];
+      q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w;
+    }
+    float4 g;
+    g.x = c * (q.x - MASS * __expf(a.x * inv_temp - lse));
+    g.y = c * (q.y - MASS * __expf(a.y * inv_temp - lse));
+    g.z = c * (q.z - MASS * __expf(a.z * inv_temp - lse));
+    g.w = c * (q.w - MASS * __expf(a.w * inv_temp - lse));
     if constexpr (sizeof(OutT) == 4) {
       reinterpret_cast<float4*>(drow)[i] = g;
     } else {
@@ -524,6 +593,24 @@ int ssl_soft_ce_bwd(const float* sp, int64_t lds, int rows, int K, const float* 
   return 0;
 }
 
+int ssl_soft_ce_fwd_bwd(const float* sp, int64_t lds, int rows, int K, const float* t0, const float* t1, int64_t ldt,
+                        int t_rows, const float* w_row, float w_fwd, float w_bwd, float inv_temp, const float* gscale,
+                        float* row_loss, void* ds, int64_t ldd, int ds_is_bf16, cudaStream_t s) {
+  if (int rc = soft_ce_check(sp, lds, rows, K, t0, t1, ldt, t_rows)) return rc;
+  APLA_CHECK(ds != nullptr && ldd % 4 == 0 && aligned16(ds), "soft_ce_fwd_bwd: ds rows must be 16-byte aligned");
+  if (rows == 0) return 0;
+  if (ds_is_bf16)
+    soft_ce_fused_kernel<__nv_bfloat16><<<rows, kRowThreads, 0, s>>>(sp, lds, K, t0, t1, ldt, t_rows, w_row, w_fwd, w_bwd,
+                                                                    inv_temp, gscale, row_loss,
+                                                                    reinterpret_cast<__nv_bfloat16*>(ds), ldd);
+  else
+    soft_ce_fused_kernel<float><<<rows, kRowThreads, 0, s>>>(sp, lds, K, t0, t1, ldt, t_rows, w_row, w_fwd, w_bwd,
+                                                            inv_temp, gscale, row_loss, reinterpret_cast<float*>(ds), ldd);
+  count_launch();
+  APLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int ssl_sum_f32(const float* a, int n, float scale, float* out, cudaStream_t s) {
   APLA_CHECK(n >= 0, "sum_f32: n=%d", n);
   sum_f32_kernel<<<1, 1024, 0, s>>>(a, n, scale, out);
@@ -652,16 +739,26 @@ int ssl_objective(const float* s_scores, int64_t lds, const float* t_scores, int
   for (int i = 0; i < 3; ++i) {
     const Term& t = term[i];
     const float* sp = s_scores + int64_t(t.r0) * lds;
-    if (int rc = ssl_soft_ce_fwd(sp, lds, t.n, K, t.t0, t.t1, ldp, t.t_rows, t.w, t.scale, inv_st, row_loss + t.r0,
-                                 lse + t.r0, mass + t.r0, s))
-      return rc;
-    if (int rc = ssl_sum_f32(row_loss + t.r0, t.n, 1.f, losses + i, s)) return rc;
-    if (ds != nullptr) {
+    // one launch per term when the gradient is wanted (second read of the rows from L2); APLA_SSL_SPLIT_CE=1 keeps the
+    // two-kernel form for A/B measurements
+    static const bool split = [] { const char* e = getenv("APLA_SSL_SPLIT_CE"); return e && atoi(e) != 0; }();
+    if (ds != nullptr && !split) {
       void* dp = reinterpret_cast<char*>(ds) + size_t(t.r0) * size_t(ldd) * esz;
-      if (int rc = ssl_soft_ce_bwd(sp, lds, t.n, K, t.t0, t.t1, ldp, t.t_rows, t.w, t.scale * t.weight, inv_st, lse + t.r0,
-                                   mass + t.r0, gscale, dp, ldd, ds_is_bf16, s))
+      if (int rc = ssl_soft_ce_fwd_bwd(sp, lds, t.n, K, t.t0, t.t1, ldp, t.t_rows, t.w, t.scale, t.scale * t.weight, inv_st,
+                                       gscale, row_loss + t.r0, dp, ldd, ds_is_bf16, s))
         return rc;
+    } else {
+      if (int rc = ssl_soft_ce_fwd(sp, lds, t.n, K, t.t0, t.t1, ldp, t.t_rows, t.w, t.scale, inv_st, row_loss + t.r0,
+                                   lse + t.r0, mass + t.r0, s))
+        return rc;
+      if (ds != nullptr) {
+        void* dp = reinterpret_cast<char*>(ds) + size_t(t.r0) * size_t(ldd) * esz;
+        if (int rc = ssl_soft_ce_bwd(sp, lds, t.n, K, t.t0, t.t1, ldp, t.t_rows, t.w, t.scale * t.weight, inv_st,
+                                     lse + t.r0, mass + t.r0, gscale, dp, ldd, ds_is_bf16, s))
+          return rc;
+      }
     }
+    if (int rc = ssl_sum_f32(row_loss + t.r0, t.n, 1.f, losses + i, s)) return rc;
   }
   return 0;
 }

@@ -179,6 +179,12 @@ int apla_soft_ce_bwd(const float* s, int64_t lds, int rows, int K, const float* 
                      int t_rows, const float* w_row, float w_uniform, float inv_temp, const float* lse,
                      const float* mass, const float* gscale, void* ds, int64_t ldd, int ds_is_bf16,
                      apla_stream_t stream);
+/* apla_soft_ce_fwd + apla_soft_ce_bwd of the same rows in ONE launch, for callers that know the upstream gradient when the
+ * loss is taken (apla_ssl_objective): the second pass walks each row backwards so that it re-reads from L2 what the first
+ * pass just streamed.  row_loss uses w_fwd, ds uses w_bwd (loss_dict scale vs. scale x loss weight). */
+int apla_soft_ce_fwd_bwd(const float* s, int64_t lds, int rows, int K, const float* t0, const float* t1, int64_t ldt,
+                         int t_rows, const float* w_row, float w_fwd, float w_bwd, float inv_temp, const float* gscale,
+                         float* row_loss, void* ds, int64_t ldd, int ds_is_bf16, apla_stream_t stream);
 /* out[0] = scale * sum a[0..n) (single CTA, fixed order): the .mean() / .sum() that end the losses. */
 int apla_sum_f32(const float* a, int n, float scale, float* out, apla_stream_t stream);
 /* y = x / max(||x||, eps) per row of x[rows,d] (f32 or bf16), y as bf16 and / or f32 (either may be NULL):
@@ -204,7 +210,7 @@ int apla_koleo_bwd(const float* x, const float* xn, int groups, int n, int D, fl
                    const int32_t* nn, const float* dist, const float* gscale, float* dx, apla_stream_t stream);
 /* teacher[n] = m teacher + (1 - m) student: DINOv2.update_teacher models.py:437-447. */
 int apla_ema_update(float* teacher, const float* student, int64_t n, float m, apla_stream_t stream);
-/* The objective of one self-supervised step on given head outputs as ONE native launch sequence (13 launches, no host code
+/* The objective of one self-supervised step on given head outputs as ONE native launch sequence (12 launches, no host code
  * between them): teacher targets + centre statistics + forward and backward of dino_local / dino_global / ibot with the
  * scales of DINOv2.forward (models.py:227-234, 237-318, 374-433; two global crops, shared head, "centering").
  *   s_scores [n_local*B + 2B + n_masked, K]: student head output = local CLS rows (crop-major), global CLS rows, masked rows;

@@ -21,7 +21,7 @@ ENTRY = {  # C-ABI name -> launcher in namespace apla
     "apla_soft_ce_fwd": "ssl_soft_ce_fwd", "apla_soft_ce_bwd": "ssl_soft_ce_bwd", "apla_sum_f32": "ssl_sum_f32",
     "apla_l2norm_fwd": "ssl_l2norm_fwd", "apla_l2norm_bwd": "ssl_l2norm_bwd", "apla_weightnorm_fwd": "ssl_weightnorm_fwd",
     "apla_weightnorm_bwd": "ssl_weightnorm_bwd", "apla_koleo_fwd": "ssl_koleo_fwd", "apla_koleo_bwd": "ssl_koleo_bwd",
-    "apla_ema_update": "ssl_ema", "apla_ssl_objective": "ssl_objective",
+    "apla_ema_update": "ssl_ema", "apla_ssl_objective": "ssl_objective", "apla_soft_ce_fwd_bwd": "ssl_soft_ce_fwd_bwd",
 }
 
 
@@ -52,7 +52,7 @@ def rewrite(src: str) -> str:
         return f"emu_launch({cfg[0]}, {cfg[1]}, {cfg[2]}, [&] {{ {m.group(1)}({m.group(3)}); }});"
 
     out = re.sub(r"([A-Za-z_]\w*(?:<[^<>;]*>)?)\s*<<<(.*?)>>>\s*\((.*?)\);", launch, src, flags=re.S)
-    assert "<<<" not in out and n_launch >= 14, n_launch
+    assert "<<<" not in out and n_launch >= 16, n_launch
     out, n = re.subn(r"extern\s+__shared__\s+float\s+sm\[\];", "float* sm = emu_dyn_smem;", out)
     assert n == 2, n
     out = out.replace('#include "common.cuh"', '#include "cuda_emu.h"').replace('#include "kernels.cuh"', "")

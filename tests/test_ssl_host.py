@@ -399,6 +399,7 @@ def test_c_abi_argument_checks_without_a_gpu():
         "apla_center_ema": (None, None, 0, 1.0, 0.9, None),                                     # K = 0
         "apla_soft_ce_fwd": (None, 0, 1, 6, None, None, 0, 1, None, 1.0, 10.0, None, None, None, None),
         "apla_soft_ce_bwd": (None, 0, 1, 8, None, None, 0, 0, None, 1.0, 10.0, None, None, None, None, 0, 0, None),
+        "apla_soft_ce_fwd_bwd": (None, 0, 1, 8, None, None, 0, 1, None, 1.0, 1.0, 10.0, None, None, None, 0, 0, None),  # no ds
         "apla_sum_f32": (None, -1, 1.0, None, None),
         "apla_l2norm_fwd": (None, 0, 1, 1, 0, 1e-12, None, None, 0, None),                      # d = 0
         "apla_l2norm_bwd": (None, 0, 1, None, 0, 1, 1, 0, 1e-12, None, 0, None),
