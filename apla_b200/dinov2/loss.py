@@ -216,16 +216,16 @@ class iBOTPatchLoss(nn.Module):
 
 class _KoLeo(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, eps):
-        loss, xn, nn_idx, d = ops.koleo_fwd(x, eps)
+    def forward(ctx, x, eps, groups):
+        loss, xn, nn_idx, d = ops.koleo_fwd(x, eps, groups)
         ctx.save_for_backward(x, xn, nn_idx, d)
-        ctx.eps = eps
+        ctx.eps, ctx.groups = eps, groups
         return loss
 
     @staticmethod
     def backward(ctx, g):
         x, xn, nn_idx, d = ctx.saved_tensors
-        return ops.koleo_bwd(x, xn, nn_idx, d, ctx.eps, g.contiguous()), None
+        return ops.koleo_bwd(x, xn, nn_idx, d, ctx.eps, g.contiguous(), ctx.groups), None, None
 
 
 class KoLeoLoss(nn.Module):
@@ -235,7 +235,14 @@ class KoLeoLoss(nn.Module):
         super().__init__()
 
     def forward(self, student_output, eps=1e-8):
-        return _KoLeo.apply(student_output.contiguous(), eps)
+        return _KoLeo.apply(student_output.contiguous(), eps, 1)
+
+    def forward_chunks(self, student_output, chunks, eps=1e-8):
+        """sum(self(p) for p in student_output.chunk(chunks)) -- what DINOv2.forward computes over the two global crops
+        (models.py:414-416) -- in one set of launches: every chunk is an independent group of rows."""
+        if student_output.shape[0] % chunks:
+            raise RuntimeError("forward_chunks needs equally sized chunks")
+        return _KoLeo.apply(student_output.contiguous(), eps, chunks)
 
 
 @torch.no_grad()

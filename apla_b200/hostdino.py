@@ -232,7 +232,9 @@ class SSLMetaArch(nn.Module):
             loss_dict["dino_local_crops_loss"] = losses[0]
         total = ce
         if self.koleo_loss_weight > 0:
-            k = self.koleo_loss_weight * sum(self.koleo_loss(p) for p in s_glob["x_norm_clstoken"].chunk(2))
+            cls = s_glob["x_norm_clstoken"]
+            k = self.koleo_loss_weight * (self.koleo_loss.forward_chunks(cls, 2) if hasattr(self.koleo_loss, "forward_chunks")
+                                          else sum(self.koleo_loss(p) for p in cls.chunk(2)))
             loss_dict["koleo_loss"] = k / 2
             total = total + k
         return total, loss_dict

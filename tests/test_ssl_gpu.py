@@ -149,6 +149,19 @@ def test_koleo(n, Dm):
     assert rel(out, ref) < 1e-4 and rel(xd.grad, a.grad) < 1e-3
 
 
+def test_koleo_chunks():
+    """KoLeoLoss.forward_chunks(x, 2) == sum of the loss over x.chunk(2) (models.py:414-416), gradients included."""
+    D, ops = _dinov2()
+    x = gen(2 * 7, 40, seed=22)
+    a = x.clone().requires_grad_(True)
+    ref = sum(S.koleo_loss(p) for p in a.chunk(2)) * 0.1
+    ref.backward()
+    xd = x.to(DEV).requires_grad_(True)
+    out = D.KoLeoLoss().forward_chunks(xd, 2) * 0.1
+    out.backward()
+    assert rel(out, ref) < 1e-4 and rel(xd.grad, a.grad) < 1e-3
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_l2norm(dtype):
     D, ops = _dinov2()
