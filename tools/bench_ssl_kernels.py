@@ -89,6 +89,18 @@ def main():
                 timeit(lambda: ops.soft_ce_bwd(s, t0, t1, t_rows, wr, 1.0 / rows, 10.0, res[1], res[2], g, dt), flush),
                 rows * K * (f4 * (1 + nt) + nb))
         del s, res
+    # the whole objective as one native launch sequence (APLA_SSL_SPLIT_CE=1 in the environment = two-kernel CE form)
+    n_s, n_t = NL * B + 2 * B + NP, 2 * B + NP
+    s_all, t_all = torch.randn(n_s, K, device=dev), torch.randn(n_t, K, device=dev)
+    dc, ic = torch.zeros(1, K, device=dev), torch.zeros(1, 1, K, device=dev)
+    mw = torch.rand(NP, device=dev)
+    form = "split CE" if os.environ.get("APLA_SSL_SPLIT_CE", "0") not in ("", "0") else "one-launch CE"
+    # algorithmic bytes: teacher rows read + probs written (+ read once for the column sums), student rows read once,
+    # teacher probs read once per consuming row group, bf16 ds written
+    nbytes = n_t * K * f4 * 3 + n_s * K * f4 + (2 * B * 2 + NP) * K * f4 + n_s * K * 2
+    rec(f"ssl_objective ({form}), bf16 ds", timeit(lambda: ops.ssl_objective(s_all, t_all, dc, ic, mw, B, NL, 0.05), flush, iters=5),
+        nbytes, 12 if form == "one-launch CE" else 15)
+    del s_all, t_all
     # head tail: L2 normalisation of the bottleneck rows, weight normalisation of the last layer
     rows = NL * B + 2 * B + NP
     z = torch.randn(rows, a.bottleneck, device=dev).bfloat16()

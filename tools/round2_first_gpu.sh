@@ -9,6 +9,7 @@ APLA_B200_SSL_STRICT=1 timeout 600 python -m pytest tests/test_ssl_gpu.py -q -m 
 APLA_B200_SSL_STRICT=1 timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_ssl_gpu.py -q -m gpu \
     -k "not 65536 and not 1048576" 2>&1 | tail -40 > gpurun_out/ssl_r2_memcheck.txt
 timeout 600 python tools/bench_ssl_kernels.py > gpurun_out/ssl_r2_kernels.jsonl 2> gpurun_out/ssl_r2_kernels.err
+APLA_SSL_SPLIT_CE=1 timeout 600 python tools/bench_ssl_kernels.py 2> /dev/null | grep ssl_objective >> gpurun_out/ssl_r2_kernels.jsonl
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 200 \
     --csv --log-file gpurun_out/ssl_r2_launches.csv python tools/bench_ssl_kernels.py > /dev/null 2>&1
 tail -5 gpurun_out/ssl_r2_pytest.txt; tail -3 gpurun_out/ssl_r2_memcheck.txt; cat gpurun_out/ssl_r2_kernels.jsonl
