@@ -86,7 +86,7 @@ def test_two_rank_gradient_mean_equals_concatenated_batch(tmp_path):
 # centres of the self-supervised losses under data parallel ("C4 additionally all-reduces two 65 536-float
 # centres asynchronously"): host logic of apla_b200/dinov2/loss.py with the kernels emulated (tests/test_ssl_host.py)
 # ---------------------------------------------------------------------------------------------------------------------
-def _centre_worker(rank, world, port, out):
+def _centre_worker(rank, world, port, out, precomputed=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -107,9 +107,13 @@ def _centre_worker(rank, world, port, out):
         n_masked = 5 + 3 * rank                              # ranks hold different numbers of masked patches
         t_cls, t_patch = torch.randn(8, K, generator=g), torch.randn(1, n_masked, K, generator=g)
         got_d = dl.softmax_center_teacher(t_cls, 0.05)
-        dl.update_center(t_cls)
         got_i = il.softmax_center_teacher(t_patch, 0.05)
-        il.update_center(t_patch)
+        if precomputed:          # the fused step form: apla_ssl_objective hands the statistics over (hostdino._forward_fused)
+            dl.register_center_stat(host.FakeOps.colsum(t_cls), len(t_cls))
+            il.register_center_stat(host.FakeOps.colsum(t_patch[0], 1.0 / n_masked), 1)
+        else:
+            dl.update_center(t_cls)
+            il.update_center(t_patch)
         errs.append(float((got_d - S.softmax_center_teacher(t_cls, dc, 0.05)).abs().max()))
         errs.append(float((got_i - S.softmax_center_teacher(t_patch, ic, 0.05)).abs().max()))
         # what the reference computes: all-reduced row sum / (len * world) for DINO, mean over ranks of the per-rank
@@ -128,8 +132,9 @@ def _centre_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_two_rank_centre_updates(tmp_path):
+@pytest.mark.parametrize("precomputed", [False, True], ids=["update_center", "register_center_stat"])
+def test_two_rank_centre_updates(tmp_path, precomputed):
     out = str(tmp_path / "centres.pt")
-    mp.spawn(_centre_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_centre_worker, args=(2, _free_port(), out, precomputed), nprocs=2, join=True)
     res = torch.load(out)
     assert max(res["errs"]) < 1e-5, res
