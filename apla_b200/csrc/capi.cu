@@ -174,6 +174,14 @@ int apla_soft_ce_fwd_bwd(const float* s, int64_t lds, int rows, int K, const flo
   return ssl_soft_ce_fwd_bwd(s, lds, rows, K, t0, t1, ldt, t_rows, w_row, w_fwd, w_bwd, inv_temp, gscale, row_loss, ds, ldd,
                              ds_is_bf16, S(stream));
 }
+int apla_sk_exp(const float* t, int64_t ldt, float inv_temp, int rows, int K, float* out, int64_t ldo,
+                apla_stream_t stream) {
+  return ssl_sk_exp(t, ldt, inv_temp, rows, K, out, ldo, S(stream));
+}
+int apla_sk_normalize(float* p, int64_t ld, int rows, int K, const float* colsum, float col_scale, float row_scale,
+                      apla_stream_t stream) {
+  return ssl_sk_normalize(p, ld, rows, K, colsum, col_scale, row_scale, S(stream));
+}
 int apla_sum_f32(const float* a, int n, float scale, float* out, apla_stream_t stream) {
   return ssl_sum_f32(a, n, scale, out, S(stream));
 }

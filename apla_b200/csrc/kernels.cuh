@@ -85,6 +85,9 @@ int ssl_soft_ce_bwd(const float* sp, int64_t lds, int rows, int K, const float* 
 int ssl_soft_ce_fwd_bwd(const float* sp, int64_t lds, int rows, int K, const float* t0, const float* t1, int64_t ldt,
                         int t_rows, const float* w_row, float w_fwd, float w_bwd, float inv_temp, const float* gscale,
                         float* row_loss, void* ds, int64_t ldd, int ds_is_bf16, cudaStream_t s);
+int ssl_sk_exp(const float* t, int64_t ldt, float inv_temp, int rows, int K, float* out, int64_t ldo, cudaStream_t s);
+int ssl_sk_normalize(float* p, int64_t ld, int rows, int K, const float* colsum, float col_scale, float row_scale,
+                     cudaStream_t s);
 int ssl_sum_f32(const float* a, int n, float scale, float* out, cudaStream_t s);
 int ssl_l2norm_fwd(const void* x, int64_t ldx, int x_is_f32, int rows, int d, float eps, void* y_bf16, float* y_f32,
                    int64_t ldy, cudaStream_t s);

@@ -299,6 +299,51 @@ soft_ce_fused_kernel(const float* __restrict__ s, int64_t lds, int K, const floa
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Sinkhorn-Knopp teacher targets (dino_clstoken_loss.py:33-60, ibot_patch_loss.py:53-83) in the [samples, K] layout:
+//   sk_exp        P = exp(t * inv_temp)
+//   sk_normalize  one iteration on a row: p_k <- p_k * col_scale / colsum[k]  (each prototype's mass -> 1/K), then
+//                 p_k <- p_k * row_scale / sum_k p_k  (each sample's mass -> row_scale); the column sums come from
+//                 colsum_f32 (+ the data-parallel all-reduce).  The reference's initial division by the total mass
+//                 cancels in the first column normalisation and is not performed.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowThreads)
+sk_exp_kernel(const float* __restrict__ t, int64_t ldt, float inv_temp, int K, float* __restrict__ out, int64_t ldo) {
+  const int64_t row = blockIdx.x;
+  const float4* tr = reinterpret_cast<const float4*>(t + row * ldt);
+  float4* orow = reinterpret_cast<float4*>(out + row * ldo);
+  const int nv = K >> 2;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    float4 a = tr[i];
+    a.x = __expf(a.x * inv_temp); a.y = __expf(a.y * inv_temp); a.z = __expf(a.z * inv_temp); a.w = __expf(a.w * inv_temp);
+    orow[i] = a;
+  }
+}
+
+__global__ void __launch_bounds__(kRowThreads)
+sk_normalize_kernel(float* __restrict__ p, int64_t ld, int K, const float* __restrict__ colsum, float col_scale,
+                    float row_scale) {
+  __shared__ float red[33];
+  const int64_t row = blockIdx.x;
+  float4* pr = reinterpret_cast<float4*>(p + row * ld);
+  const float4* cs = reinterpret_cast<const float4*>(colsum);
+  const int nv = K >> 2;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const float4 a = pr[i];
+    const float4 c = __ldg(cs + i);
+    acc += (a.x * (col_scale / c.x) + a.y * (col_scale / c.y)) + (a.z * (col_scale / c.z) + a.w * (col_scale / c.w));
+  }
+  const float inv = row_scale / block_sum(acc, red);
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    float4 a = pr[i];
+    const float4 c = __ldg(cs + i);
+    a.x = a.x * (col_scale / c.x) * inv; a.y = a.y * (col_scale / c.y) * inv;
+    a.z = a.z * (col_scale / c.z) * inv; a.w = a.w * (col_scale / c.w) * inv;
+    pr[i] = a;
+  }
+}
+
 // out[0] = scale * sum_i a[i] in a fixed order (single CTA)
 __global__ void __launch_bounds__(1024) sum_f32_kernel(const float* __restrict__ a, int n, float scale, float* __restrict__ out) {
   __shared__ float red[33];
@@ -606,6 +651,27 @@ int ssl_soft_ce_fwd_bwd(const float* sp, int64_t lds, int rows, int K, const flo
   else
     soft_ce_fused_kernel<float><<<rows, kRowThreads, 0, s>>>(sp, lds, K, t0, t1, ldt, t_rows, w_row, w_fwd, w_bwd,
                                                             inv_temp, gscale, row_loss, reinterpret_cast<float*>(ds), ldd);
+  count_launch();
+  APLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ssl_sk_exp(const float* t, int64_t ldt, float inv_temp, int rows, int K, float* out, int64_t ldo, cudaStream_t s) {
+  APLA_CHECK(rows >= 0 && K > 0 && K % 4 == 0, "sk_exp: K=%d must be a positive multiple of 4", K);
+  APLA_CHECK(ldt % 4 == 0 && ldo % 4 == 0 && aligned16(t) && aligned16(out), "sk_exp: rows must be 16-byte aligned");
+  if (rows == 0) return 0;
+  sk_exp_kernel<<<rows, kRowThreads, 0, s>>>(t, ldt, inv_temp, K, out, ldo);
+  count_launch();
+  APLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ssl_sk_normalize(float* p, int64_t ld, int rows, int K, const float* colsum, float col_scale, float row_scale,
+                     cudaStream_t s) {
+  APLA_CHECK(rows >= 0 && K > 0 && K % 4 == 0, "sk_normalize: K=%d must be a positive multiple of 4", K);
+  APLA_CHECK(ld % 4 == 0 && aligned16(p) && aligned16(colsum), "sk_normalize: rows must be 16-byte aligned");
+  if (rows == 0) return 0;
+  sk_normalize_kernel<<<rows, kRowThreads, 0, s>>>(p, ld, K, colsum, col_scale, row_scale);
   count_launch();
   APLA_CUDA(cudaGetLastError());
   return 0;

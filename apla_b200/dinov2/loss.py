@@ -13,7 +13,8 @@ Differences from the reference, all deliberate:
   * `center` is updated IN PLACE (the reference rebinds the buffer to a new tensor every step);
   * the [rows, K] log-softmax and the teacher / student product are never materialised: one kernel per loss call reads the
     scores once for the forward (per-row log-sum-exp kept) and once for the backward;
-  * Sinkhorn-Knopp centring is not provided (no shipped config selects it): the methods raise NotImplementedError.
+  * `sinkhorn_knopp_teacher` skips the reference's first division by the total mass (it cancels in the first column
+    normalisation); `int(B)` of the iBOT variant is one host read of a one-element tensor, as in the reference's `Q /= B`.
 Tested against oracle/ssl_oracle.py (itself pinned to the reference) in tests/test_ssl_gpu.py.
 STATUS: not yet run on hardware; verified on the CPU-emulated kernels (see csrc/ssl.cu, tests/test_ssl_emu.py)."""
 from __future__ import annotations
@@ -79,7 +80,9 @@ class DINOLoss(nn.Module):
 
     @torch.no_grad()
     def sinkhorn_knopp_teacher(self, teacher_output, teacher_temp, n_iterations=3):
-        raise NotImplementedError("Sinkhorn-Knopp centring has no B200 path (no shipped config uses it)")
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        return ops.sinkhorn_knopp(teacher_output, teacher_temp, n_iterations, teacher_output.shape[0] * world,
+                                  dist.all_reduce if dist.is_initialized() else None)
 
     def forward(self, student_output_list, teacher_out_softmaxed_centered_list):
         """- sum over (student crop, teacher crop) pairs of mean_b sum_k t log_softmax(s / student_temp)."""
@@ -156,7 +159,13 @@ class iBOTPatchLoss(nn.Module):
 
     @torch.no_grad()
     def sinkhorn_knopp_teacher(self, teacher_output, teacher_temp, n_masked_patches_tensor, n_iterations=3):
-        raise NotImplementedError("Sinkhorn-Knopp centring has no B200 path (no shipped config uses it)")
+        """B = the number of masked patches over all ranks (ibot_patch_loss.py:58-59; the reference all-reduces it even
+        outside a process group, which raises -- here a single process is world size 1)."""
+        B = n_masked_patches_tensor
+        if dist.is_initialized():
+            dist.all_reduce(B)
+        return ops.sinkhorn_knopp(teacher_output, teacher_temp, n_iterations, int(B),
+                                  dist.all_reduce if dist.is_initialized() else None)
 
     def forward(self, student_patch_tokens, teacher_patch_tokens, student_masks_flat):
         """Dense form (B, N, K): - mean_b sum_n mask_bn sum_k t log_softmax(s / T) / max(sum_n mask_bn, 1)."""

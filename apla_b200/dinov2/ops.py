@@ -66,6 +66,24 @@ def center_ema_(center: torch.Tensor, batch_sum: torch.Tensor, count: float, mom
     return center
 
 
+def sinkhorn_knopp(teacher_output: torch.Tensor, teacher_temp: float, n_iterations: int, n_samples_world: int,
+                   all_reduce=None) -> torch.Tensor:
+    """Sinkhorn-Knopp targets [n, K] (rows sum to 1) from teacher scores [n, K]; `all_reduce(t)` sums a tensor over the
+    ranks in place (None = single process); `n_samples_world` = B of the reference (samples over all ranks)."""
+    require_device()
+    t = _rows(teacher_output, "teacher_output")
+    n, K = t.shape
+    P = torch.empty(n, K, device=t.device, dtype=F32)
+    LIB.call("apla_sk_exp", ptr(t), t.stride(0), 1.0 / float(teacher_temp), n, K, ptr(P), P.stride(0), stream())
+    for it in range(n_iterations):
+        cs = colsum(P)
+        if all_reduce is not None:
+            all_reduce(cs)
+        row_scale = 1.0 if it + 1 == n_iterations else 1.0 / float(n_samples_world)
+        LIB.call("apla_sk_normalize", ptr(P), P.stride(0), n, K, ptr(cs), 1.0 / K, row_scale, stream())
+    return P
+
+
 def soft_ce_fwd(s, t0, t1, t_rows, w_row, w_uniform, inv_temp) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """-> (loss scalar, lse [rows], mass [rows])."""
     require_device()

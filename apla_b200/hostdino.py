@@ -131,7 +131,7 @@ class SSLMetaArch(nn.Module):
     def __init__(self, student_backbone: nn.Module, teacher_backbone: nn.Module, student_head: nn.Module,
                  teacher_head: nn.Module, out_dim: int, *, n_global_crops: int = 2, n_local_crops: int = 8,
                  dino_loss_weight: float = 1.0, koleo_loss_weight: float = 0.1, ibot_loss_weight: float = 1.0,
-                 loss_classes=None, fused_objective: bool = False):
+                 loss_classes=None, fused_objective: bool = False, centering: str = "centering"):
         super().__init__()
         if n_global_crops != 2:
             raise AssertionError("the objective is written for two global crops (models.py:214)")
@@ -151,6 +151,12 @@ class SSLMetaArch(nn.Module):
         # True: student head + the three cross-entropy terms as ONE autograd node over `apla_ssl_objective`
         # (DINOHead.forward_with_objective); False: the reference's call structure, one loss-class call per term
         self.fused_objective = fused_objective
+        if centering not in ("centering", "sinkhorn_knopp"):
+            raise NotImplementedError(centering)                                         # models.py:317-318
+        if centering == "sinkhorn_knopp" and fused_objective:
+            raise ValueError("the fused objective implements softmax-centre targets; use the per-term form with "
+                             "centering='sinkhorn_knopp'")
+        self.centering = centering
 
     def forward(self, images: Dict[str, torch.Tensor], teacher_temp: float):
         dev = next(self.student.parameters()).device
@@ -177,12 +183,19 @@ class SSLMetaArch(nn.Module):
         if self.fused_objective:
             return self._forward_fused(t_out, global_crops, local_crops, masks, mask_indices, masks_weight, teacher_temp)
         with torch.no_grad():
-            t_dino = self.dino_loss.softmax_center_teacher(t_cls_out, teacher_temp=teacher_temp) \
-                .view(ng, -1, t_cls_out.shape[-1])
-            self.dino_loss.update_center(t_cls_out)
-            t_ibot = self.ibot_patch_loss.softmax_center_teacher(t_patch_out.unsqueeze(0), teacher_temp=teacher_temp) \
-                .squeeze(0)
-            self.ibot_patch_loss.update_center(t_patch_out.unsqueeze(0))
+            if self.centering == "sinkhorn_knopp":                                        # models.py:303-315
+                t_dino = self.dino_loss.sinkhorn_knopp_teacher(t_cls_out, teacher_temp=teacher_temp) \
+                    .view(ng, -1, t_cls_out.shape[-1])
+                t_ibot = self.ibot_patch_loss.sinkhorn_knopp_teacher(
+                    t_patch_out, teacher_temp=teacher_temp,
+                    n_masked_patches_tensor=images["n_masked_patches"].to(dev).clone())
+            else:                                                                         # "centering", models.py:288-301
+                t_dino = self.dino_loss.softmax_center_teacher(t_cls_out, teacher_temp=teacher_temp) \
+                    .view(ng, -1, t_cls_out.shape[-1])
+                self.dino_loss.update_center(t_cls_out)
+                t_ibot = self.ibot_patch_loss.softmax_center_teacher(t_patch_out.unsqueeze(0),
+                                                                     teacher_temp=teacher_temp).squeeze(0)
+                self.ibot_patch_loss.update_center(t_patch_out.unsqueeze(0))
 
         # ---- student (:322-371): [masked global | local] crops in one packed pass, one head pass over all rows
         s_glob, s_loc = self.student["backbone"]([global_crops, local_crops], masks=[masks, None], is_training=True)

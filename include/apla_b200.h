@@ -185,6 +185,14 @@ int apla_soft_ce_bwd(const float* s, int64_t lds, int rows, int K, const float* 
 int apla_soft_ce_fwd_bwd(const float* s, int64_t lds, int rows, int K, const float* t0, const float* t1, int64_t ldt,
                          int t_rows, const float* w_row, float w_fwd, float w_bwd, float inv_temp, const float* gscale,
                          float* row_loss, void* ds, int64_t ldd, int ds_is_bf16, apla_stream_t stream);
+/* Sinkhorn-Knopp teacher targets, sinkhorn_knopp_teacher loss/dino_clstoken_loss.py:33-60, loss/ibot_patch_loss.py:53-83,
+ * in the [samples, K] layout: out = exp(t * inv_temp); then per iteration apla_colsum_f32 (+ all-reduce) and
+ * apla_sk_normalize: p[b,k] <- p[b,k] * col_scale / colsum[k] (col_scale = 1/K), then p[b,:] <- p[b,:] * row_scale / sum_k p[b,k]
+ * (row_scale = 1/B between iterations, 1 after the last so that every sample's targets sum to 1). */
+int apla_sk_exp(const float* t, int64_t ldt, float inv_temp, int rows, int K, float* out, int64_t ldo,
+                apla_stream_t stream);
+int apla_sk_normalize(float* p, int64_t ld, int rows, int K, const float* colsum, float col_scale, float row_scale,
+                      apla_stream_t stream);
 /* out[0] = scale * sum a[0..n) (single CTA, fixed order): the .mean() / .sum() that end the losses. */
 int apla_sum_f32(const float* a, int n, float scale, float* out, apla_stream_t stream);
 /* y = x / max(||x||, eps) per row of x[rows,d] (f32 or bf16), y as bf16 and / or f32 (either may be NULL):

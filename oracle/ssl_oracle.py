@@ -29,7 +29,8 @@ teacher after the EMA and both centres, <= 2e-5).  The reference's ``models.py``
 that generator supplies ``tests/golden/xformers_shim.py`` (plain-torch ``memory_efficient_attention``, ``unbind``,
 ``BlockDiagonalMask``): **pinned modulo the xformers shim** -- the kernels of xformers 0.0.18 themselves and its
 ``cross_entropy`` (the reference's own fallback, ibot_patch_loss.py:26-27, is what ran) are the unpinned residue.
-Sinkhorn-Knopp centring (dino_clstoken_loss.py:33-60) is not restated: every shipped config uses "centering".
+Sinkhorn-Knopp centring (``sinkhorn_knopp_teacher``, dino_clstoken_loss.py:33-60, ibot_patch_loss.py:53-83; no shipped config
+selects it) is restated as ``sinkhorn_knopp`` and pinned by ``tests/golden/make_golden_ssl_sk.py`` -> ``ssl_sk_small``.
 """
 from __future__ import annotations
 
@@ -75,6 +76,25 @@ def dino_head_forward(sd: Dict[str, Tensor], x: Tensor, prefix: str = "") -> Ten
 def softmax_center_teacher(teacher_out: Tensor, center: Tensor, teacher_temp: float) -> Tensor:
     """dino_clstoken_loss.py:28-31 / ibot_patch_loss.py:39-51 (after the pending centre update has been applied)."""
     return F.softmax((teacher_out - center) / teacher_temp, dim=-1)
+
+
+def sinkhorn_knopp(teacher_out: Tensor, teacher_temp: float, n_iterations: int = 3, n_samples_world: Optional[int] = None,
+                   all_reduce=None) -> Tensor:
+    """dino_clstoken_loss.py:33-60 / ibot_patch_loss.py:53-83, in the [samples, K] layout (the reference works on the
+    transpose): Q = exp(t / temp) normalised to total mass 1, then n_iterations of {each prototype's mass -> 1/K, each
+    sample's mass -> 1/B}, finally x B so that every sample's row sums to 1.  ``n_samples_world`` = B (samples over all
+    ranks; iBOT passes the all-reduced number of masked patches), ``all_reduce`` = in-place sum over ranks (None = 1 rank)."""
+    red = all_reduce if all_reduce is not None else (lambda x: x)
+    Q = torch.exp(teacher_out.float() / teacher_temp)
+    B = Q.shape[0] if n_samples_world is None else n_samples_world
+    K = Q.shape[1]
+    Q = Q / red(Q.sum())
+    for _ in range(n_iterations):
+        Q = Q / red(Q.sum(dim=0, keepdim=True))
+        Q = Q / K
+        Q = Q / Q.sum(dim=1, keepdim=True)
+        Q = Q / B
+    return Q * B
 
 
 def dino_center_update(center: Tensor, teacher_out: Tensor, momentum: float = 0.9, world_size: int = 1,

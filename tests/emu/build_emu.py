@@ -22,6 +22,7 @@ ENTRY = {  # C-ABI name -> launcher in namespace apla
     "apla_l2norm_fwd": "ssl_l2norm_fwd", "apla_l2norm_bwd": "ssl_l2norm_bwd", "apla_weightnorm_fwd": "ssl_weightnorm_fwd",
     "apla_weightnorm_bwd": "ssl_weightnorm_bwd", "apla_koleo_fwd": "ssl_koleo_fwd", "apla_koleo_bwd": "ssl_koleo_bwd",
     "apla_ema_update": "ssl_ema", "apla_ssl_objective": "ssl_objective", "apla_soft_ce_fwd_bwd": "ssl_soft_ce_fwd_bwd",
+    "apla_sk_exp": "ssl_sk_exp", "apla_sk_normalize": "ssl_sk_normalize",
 }
 
 

@@ -102,6 +102,20 @@ class EmuOps:
         return center
 
     @classmethod
+    def sinkhorn_knopp(cls, t, temp, n_iterations, n_samples_world, all_reduce=None):
+        cls._rows(t, "teacher_output")
+        n, K = t.shape
+        P = _Guarded.empty(n, K)
+        keep = list(_Guarded.live)
+        cls.call("apla_sk_exp", _p(t), t.stride(0), 1.0 / temp, n, K, _p(P), P.stride(0))
+        for it in range(n_iterations):
+            cs = cls.colsum(P)
+            _Guarded.live.extend(keep)                       # P's guard bands are re-checked after the in-place pass
+            cls.call("apla_sk_normalize", _p(P), P.stride(0), n, K, _p(cs), 1.0 / K,
+                     1.0 if it + 1 == n_iterations else 1.0 / n_samples_world)
+        return P
+
+    @classmethod
     def soft_ce_fwd(cls, s, t0, t1, t_rows, w_row, w_uniform, inv_temp):
         cls._rows(s, "s"); cls._rows(t0, "t0")
         rows, K = s.shape

@@ -149,6 +149,19 @@ def test_koleo(n, Dm):
     assert rel(out, ref) < 1e-4 and rel(xd.grad, a.grad) < 1e-3
 
 
+@pytest.mark.parametrize("n,K,temp,iters", [(12, 128, 0.04, 3), (37, 512, 0.07, 1), (5, 65536, 0.04, 3)])
+def test_sinkhorn_knopp_teacher(n, K, temp, iters):
+    """DINOLoss / iBOTPatchLoss.sinkhorn_knopp_teacher against the oracle (pinned to the reference by ssl_sk_small)."""
+    D, ops = _dinov2()
+    t = gen(n, K, seed=80, scale=0.3)
+    ref = S.sinkhorn_knopp(t, temp, iters)
+    out = D.DINOLoss(K).to(DEV).sinkhorn_knopp_teacher(t.to(DEV), temp, n_iterations=iters)
+    assert rel(out, ref) < 1e-4 and float((out.sum(-1) - 1).abs().max()) < 1e-4
+    out_i = D.iBOTPatchLoss(K).to(DEV).sinkhorn_knopp_teacher(
+        t.to(DEV), temp, n_masked_patches_tensor=torch.full((1,), n, dtype=torch.long), n_iterations=iters)
+    assert rel(out_i, S.sinkhorn_knopp(t, temp, iters, n_samples_world=n)) < 1e-4
+
+
 def test_koleo_chunks():
     """KoLeoLoss.forward_chunks(x, 2) == sum of the loss over x.chunk(2) (models.py:414-416), gradients included."""
     D, ops = _dinov2()
@@ -381,8 +394,6 @@ def test_rejects_what_it_cannot_run():
         ops.softmax_center(torch.randn(4, 64, device=DEV, dtype=torch.float16), torch.zeros(1, 64, device=DEV), 0.05)
     with pytest.raises(RuntimeError):
         ops.softmax_center(torch.randn(4, 66, device=DEV), torch.zeros(1, 66, device=DEV), 0.05)   # K % 4
-    with pytest.raises(NotImplementedError):
-        D.DINOLoss(64).sinkhorn_knopp_teacher(torch.zeros(2, 64), 0.05)
     with pytest.raises(NotImplementedError):
         D.DINOHead(64, 256, use_bn=True)
     with pytest.raises(RuntimeError, match="multiples of 64"):

@@ -10,6 +10,12 @@ import os
 import pytest
 import torch
 
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().flatten(), torch.as_tensor(b).double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
@@ -38,6 +44,18 @@ class FakeOps:
     def center_ema_(center, batch_sum, count, momentum):
         center.copy_(center * momentum + batch_sum.reshape(center.shape) * (1.0 / count) * (1 - momentum))
         return center
+
+    @classmethod
+    def sinkhorn_knopp(cls, t, temp, n_iterations, n_samples_world, all_reduce=None):
+        P = torch.exp(cls._rows(t, "teacher_output") * (1.0 / temp))
+        K = P.shape[1]
+        for it in range(n_iterations):
+            cs = cls.colsum(P)
+            if all_reduce is not None:
+                all_reduce(cs)
+            P = P * ((1.0 / K) / cs)
+            P = P * ((1.0 if it + 1 == n_iterations else 1.0 / n_samples_world) / P.sum(-1, keepdim=True))
+        return P
 
     @staticmethod
     def _q(s, t0, t1, t_rows):
@@ -400,6 +418,8 @@ def test_c_abi_argument_checks_without_a_gpu():
         "apla_soft_ce_fwd": (None, 0, 1, 6, None, None, 0, 1, None, 1.0, 10.0, None, None, None, None),
         "apla_soft_ce_bwd": (None, 0, 1, 8, None, None, 0, 0, None, 1.0, 10.0, None, None, None, None, 0, 0, None),
         "apla_soft_ce_fwd_bwd": (None, 0, 1, 8, None, None, 0, 1, None, 1.0, 1.0, 10.0, None, None, None, 0, 0, None),  # no ds
+        "apla_sk_exp": (None, 0, 1.0, 1, 6, None, 0, None),
+        "apla_sk_normalize": (None, 0, 1, 6, None, 1.0, 1.0, None),
         "apla_sum_f32": (None, -1, 1.0, None, None),
         "apla_l2norm_fwd": (None, 0, 1, 1, 0, 1e-12, None, None, 0, None),                      # d = 0
         "apla_l2norm_bwd": (None, 0, 1, None, 0, 1, 1, 0, 1e-12, None, 0, None),
@@ -419,3 +439,57 @@ def test_c_abi_argument_checks_without_a_gpu():
     # a wide row buffer is refused rather than launched with too much shared memory
     assert dll.apla_koleo_fwd(None, 1, 4, 20000, 1e-8, 1.0, None, None, None, None) == 1
     assert b"too wide" in dll.apla_last_error()
+
+
+def test_meta_arch_sinkhorn_knopp_centering(monkeypatch):
+    """`centering: sinkhorn_knopp` (models.py:303-315): the step's loss with the teacher targets swapped for the
+    Sinkhorn-Knopp ones, against the same assembly done by hand over the oracle (exact arithmetic under the wiring)."""
+    import sys
+    sys.path.insert(0, HERE)
+    import helpers
+    import apla_b200.dinov2 as D
+    from apla_b200.dinov2 import dino_head, loss
+    from apla_b200.hostdino import SSLMetaArch
+    from oracle import ssl_oracle as S
+    monkeypatch.setattr(loss, "ops", FakeOps)
+    monkeypatch.setattr(dino_head, "R", ExactOps)
+    monkeypatch.setattr(dino_head, "G", ExactGemm)
+    monkeypatch.setattr(dino_head, "BF16", torch.float32)
+    cfg, student, teacher, trainable, batch, arr = helpers.ssl_step_case()
+    split = lambda sd, pre: {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}          # noqa: E731
+
+    def head_of(sd):
+        h = D.DINOHead(cfg["embed_dim"], cfg["K"], nlayers=3, hidden_dim=cfg["head_hidden"],
+                       bottleneck_dim=cfg["head_bottleneck"])
+        h.load_state_dict(split(sd, "dino_head."))
+        return h
+
+    model = SSLMetaArch(OracleDinoBackbone(split(student, "backbone."), set(), cfg),
+                        OracleDinoBackbone(split(teacher, "backbone."), set(), cfg), head_of(student), head_of(teacher),
+                        cfg["K"], n_local_crops=cfg["n_local"], koleo_loss_weight=cfg["koleo_w"],
+                        centering="sinkhorn_knopp")
+    loss_val, parts = model(batch, teacher_temp=cfg["teacher_temp"])
+    # by hand over the oracle
+    kw = dict(patch=cfg["patch"], depth=cfg["depth"], num_heads=cfg["num_heads"])
+    masks, B, nl = batch["collated_masks"], cfg["B"], cfg["n_local"]
+    idx, mw = S.mask_indices_of(masks), S.masks_weight_of(masks)
+    with torch.no_grad():
+        t = S.dinov2_backbone(teacher, batch["collated_global_crops"], None, **kw)
+        a, b = t["cls"].chunk(2)
+        t_out = S.dino_head_forward(split(teacher, "dino_head."), torch.cat((b, a, t["patch"].flatten(0, 1)[idx])))
+        t_d = S.sinkhorn_knopp(t_out[:2 * B], cfg["teacher_temp"]).view(2, B, -1)
+        t_i = S.sinkhorn_knopp(t_out[2 * B:], cfg["teacher_temp"], n_samples_world=idx.shape[0])
+        sg, sl = S.dinov2_backbone(student, [batch["collated_global_crops"], batch["collated_local_crops"]],
+                                   [masks, None], **kw)
+        s_out = S.dino_head_forward(split(student, "dino_head."),
+                                    torch.cat((sl["cls"], sg["cls"], sg["patch"].flatten(0, 1)[idx])))
+        s_l, s_g, s_p = s_out[:nl * B], s_out[nl * B:nl * B + 2 * B], s_out[nl * B + 2 * B:]
+        terms = 2 + 2 * nl
+        want = (S.dino_loss(s_l.chunk(nl), list(t_d)) / terms + S.dino_loss([s_g], [t_d.flatten(0, 1)]) * 2 / terms
+                + cfg["koleo_w"] * sum(S.koleo_loss(p) for p in sg["cls"].chunk(2))
+                + S.ibot_loss_masked(s_p, t_i, masks, n_masked_patches=idx.shape[0], masks_weight=mw))
+    assert rel(loss_val.detach(), want) < 1e-5
+    assert model.dino_loss.updated is True                       # no centre update is pending in this mode
+    with pytest.raises(ValueError):
+        SSLMetaArch(torch.nn.Identity(), torch.nn.Identity(), torch.nn.Identity(), torch.nn.Identity(), 8,
+                    centering="sinkhorn_knopp", fused_objective=True)

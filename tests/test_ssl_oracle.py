@@ -181,3 +181,13 @@ def test_ssl_step_matches_reference(golden_dir):
             assert rel(teacher[k], arr[tag + "teacher_after/" + k]) < 1e-6, (step, k)
     assert rel(dino_c, arr["final/dino_center"]) < 1e-5
     assert rel(ibot_c, arr["final/ibot_center"]) < 1e-5
+
+
+def test_sinkhorn_knopp_matches_reference(golden_dir):
+    arr = np.load(os.path.join(golden_dir, "ssl_sk_small.npz"))
+    t_cls, t_patch = torch.as_tensor(arr["t_cls"]), torch.as_tensor(arr["t_patch"])
+    assert rel(S.sinkhorn_knopp(t_cls, 0.04), arr["dino_sk_t0.04_it3"]) < 1e-5
+    assert rel(S.sinkhorn_knopp(t_cls, 0.07, n_iterations=1), arr["dino_sk_t0.07_it1"]) < 1e-5
+    assert rel(S.sinkhorn_knopp(t_patch, 0.04, n_samples_world=23), arr["ibot_sk_t0.04_it3"]) < 1e-5
+    assert rel(S.sinkhorn_knopp(t_cls, 0.04), arr["dino_sk_t0.04_it3_in_group"]) < 1e-5
+    assert float((S.sinkhorn_knopp(t_cls, 0.04).sum(-1) - 1).abs().max()) < 1e-5        # an assignment per sample
