@@ -562,6 +562,8 @@ ema_kernel_v4(float4* __restrict__ t, const float4* __restrict__ s, int64_t n4, 
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+// ds rows are written as float4 (f32) or as uint2 = four bf16
+inline bool aligned_ds(const void* p, int is_bf16) { return (reinterpret_cast<uintptr_t>(p) & (is_bf16 ? 7 : 15)) == 0; }
 
 }  // namespace
 
@@ -624,7 +626,7 @@ int ssl_soft_ce_bwd(const float* sp, int64_t lds, int rows, int K, const float* 
                     int t_rows, const float* w_row, float w_uniform, float inv_temp, const float* lse, const float* mass,
                     const float* gscale, void* ds, int64_t ldd, int ds_is_bf16, cudaStream_t s) {
   if (int rc = soft_ce_check(sp, lds, rows, K, t0, t1, ldt, t_rows)) return rc;
-  APLA_CHECK(ldd % 4 == 0 && aligned16(ds), "soft_ce_bwd: ds rows must be 16-byte aligned");
+  APLA_CHECK(ldd % 4 == 0 && aligned_ds(ds, ds_is_bf16), "soft_ce_bwd: ds rows must be 16-byte (f32) / 8-byte (bf16) aligned");
   if (rows == 0) return 0;
   if (ds_is_bf16)
     soft_ce_bwd_kernel<__nv_bfloat16><<<rows, kRowThreads, 0, s>>>(sp, lds, K, t0, t1, ldt, t_rows, w_row, w_uniform,
@@ -642,7 +644,8 @@ int ssl_soft_ce_fwd_bwd(const float* sp, int64_t lds, int rows, int K, const flo
                         int t_rows, const float* w_row, float w_fwd, float w_bwd, float inv_temp, const float* gscale,
                         float* row_loss, void* ds, int64_t ldd, int ds_is_bf16, cudaStream_t s) {
   if (int rc = soft_ce_check(sp, lds, rows, K, t0, t1, ldt, t_rows)) return rc;
-  APLA_CHECK(ds != nullptr && ldd % 4 == 0 && aligned16(ds), "soft_ce_fwd_bwd: ds rows must be 16-byte aligned");
+  APLA_CHECK(ds != nullptr && ldd % 4 == 0 && aligned_ds(ds, ds_is_bf16),
+             "soft_ce_fwd_bwd: ds rows must be 16-byte (f32) / 8-byte (bf16) aligned");
   if (rows == 0) return 0;
   if (ds_is_bf16)
     soft_ce_fused_kernel<__nv_bfloat16><<<rows, kRowThreads, 0, s>>>(sp, lds, K, t0, t1, ldt, t_rows, w_row, w_fwd, w_bwd,

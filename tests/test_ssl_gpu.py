@@ -41,7 +41,7 @@ def gen(*shape, seed=0, scale=1.0):
     return torch.randn(*shape, generator=g) * scale
 
 
-@pytest.mark.parametrize("n,K,temp", [(37, 4096, 0.07), (5, 65536, 0.04), (1, 64, 0.04)])
+@pytest.mark.parametrize("n,K,temp", [(37, 4096, 0.07), (5, 65536, 0.04), (1, 64, 0.04), (3, 4, 0.05), (2, 2052, 0.05)])
 def test_softmax_center(n, K, temp):
     D, ops = _dinov2()
     t, c = gen(n, K, seed=1), gen(1, K, seed=2, scale=0.3)
@@ -65,7 +65,8 @@ def test_center_update(n, K):
     assert rel(ci, S.ibot_center_update(c.view(1, 1, K), t.view(1, n, K), 0.9)) < 1e-5
 
 
-@pytest.mark.parametrize("B,K,n_local,merged", [(3, 64, 4, True), (3, 64, 4, False), (8, 65536, 8, True)])
+@pytest.mark.parametrize("B,K,n_local,merged", [(3, 64, 4, True), (3, 64, 4, False), (8, 65536, 8, True), (1, 4, 2, True),
+                                                 (2, 2052, 3, False)])
 def test_dino_loss_local_and_global(B, K, n_local, merged):
     D, ops = _dinov2()
     loss_mod = D.DINOLoss(K).to(DEV)
@@ -85,7 +86,7 @@ def test_dino_loss_local_and_global(B, K, n_local, merged):
     assert rel(x.grad, a.grad) < 1e-3 and rel(y.grad, b.grad) < 1e-3
 
 
-@pytest.mark.parametrize("nimg,P,K,pad", [(4, 16, 64, 3), (6, 256, 65536, 5), (4, 16, 64, 0)])
+@pytest.mark.parametrize("nimg,P,K,pad", [(4, 16, 64, 3), (6, 256, 65536, 5), (4, 16, 64, 0), (2, 4, 4, 1), (3, 9, 2052, 0)])
 def test_ibot_forward_masked(nimg, P, K, pad):
     D, ops = _dinov2()
     loss_mod = D.iBOTPatchLoss(K).to(DEV)
@@ -149,7 +150,8 @@ def test_koleo(n, Dm):
     assert rel(out, ref) < 1e-4 and rel(xd.grad, a.grad) < 1e-3
 
 
-@pytest.mark.parametrize("n,K,temp,iters", [(12, 128, 0.04, 3), (37, 512, 0.07, 1), (5, 65536, 0.04, 3)])
+@pytest.mark.parametrize("n,K,temp,iters", [(12, 128, 0.04, 3), (37, 512, 0.07, 1), (5, 65536, 0.04, 3), (2, 4, 0.05, 2),
+                                            (3, 2052, 0.05, 3)])
 def test_sinkhorn_knopp_teacher(n, K, temp, iters):
     """DINOLoss / iBOTPatchLoss.sinkhorn_knopp_teacher against the oracle (pinned to the reference by ssl_sk_small)."""
     D, ops = _dinov2()
@@ -312,7 +314,7 @@ def test_dino_head(n, in_dim, hidden, bott, K, nlayers, bias):
 
 
 @pytest.mark.parametrize("B,K,n_local,P,empty", [(3, 64, 4, 16, False), (4, 512, 8, 16, False), (2, 64, 0, 16, False),
-                                                 (3, 64, 2, 16, True)])
+                                                 (3, 64, 2, 16, True), (1, 4, 1, 4, False), (2, 2052, 2, 9, False)])
 def test_native_objective_sequence(B, K, n_local, P, empty):
     """`apla_ssl_objective` (one native launch sequence) against the oracle's `ssl_objective` on given head outputs: the
     three loss terms, the gradient with respect to every student score and both centre updates."""
