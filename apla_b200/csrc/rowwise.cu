@@ -144,6 +144,74 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld_dy, const float* 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Generic-width LayerNorm (any D % 4 == 0 that is not a multiple of 128, e.g. the 64-wide toy models of the parity
+// fixtures): same arithmetic, one warp per row, the row re-read from L1/L2 instead of held in registers.  Not a
+// performance path.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ln_fwd_generic_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
+                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int64_t ldy, int rows, int D,
+                      float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + row * ldx;
+  float s = 0.f;
+  for (int k = lane; k < D; k += 32) s += xr[k];
+  const float mean = warp_sum(s) / D;
+  float q = 0.f;
+  for (int k = lane; k < D; k += 32) q += (xr[k] - mean) * (xr[k] - mean);
+  const float rstd = rsqrtf(warp_sum(q) / D + eps);
+  for (int k = lane; k < D; k += 32) y[row * ldy + k] = __float2bfloat16_rn((xr[k] - mean) * rstd * w[k] + bias[k]);
+}
+
+__global__ void __launch_bounds__(256)
+ln_bwd_generic_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld_dy, const float* __restrict__ x, int64_t ldx,
+                      const float* __restrict__ w, const float* dres, int64_t ld_dres, float* dx, int64_t ld_dx,
+                      __nv_bfloat16* __restrict__ dxb, int64_t ld_dxb, const float* __restrict__ gamma,
+                      __nv_bfloat16* __restrict__ sub, int64_t ld_sub, const int* __restrict__ idx, int r, int r_pad,
+                      int rows, int D, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + row * ldx;
+  const __nv_bfloat16* dyr = dy + row * ld_dy;
+  float s = 0.f;
+  for (int k = lane; k < D; k += 32) s += xr[k];
+  const float mean = warp_sum(s) / D;
+  float q = 0.f;
+  for (int k = lane; k < D; k += 32) q += (xr[k] - mean) * (xr[k] - mean);
+  const float rstd = rsqrtf(warp_sum(q) / D + eps);
+  float sg = 0.f, sgx = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    const float g = __bfloat162float(dyr[k]) * w[k];
+    sg += g;
+    sgx += g * (xr[k] - mean) * rstd;
+  }
+  const float mg = warp_sum(sg) / D, mgx = warp_sum(sgx) / D;
+  // (dres may alias dx: every element is read and written by the same thread, reads first)
+  for (int k = lane; k < D; k += 32) {
+    const float g = __bfloat162float(dyr[k]) * w[k];
+    float o = rstd * (g - mg - (xr[k] - mean) * rstd * mgx);
+    if (dres) o += dres[row * ld_dres + k];
+    dx[row * ld_dx + k] = o;
+    if (dxb) dxb[row * ld_dxb + k] = __float2bfloat16_rn(gamma ? o * gamma[k] : o);
+  }
+  if (sub) {
+    __syncwarp();
+    __threadfence_block();
+    for (int j = lane; j < r_pad; j += 32) {
+      float v = 0.f;
+      if (j < r) {
+        const int c = idx[j];
+        v = dx[row * ld_dx + c] * (gamma ? gamma[c] : 1.f);
+      }
+      sub[row * ld_sub + j] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // scaled fp32 -> bf16 copy with the same gather (used where no LayerNorm precedes: nothing on the C2 path,
 // kept for the module-level API where dY arrives from autograd)
 // ------------------------------------------------------------------------------------------------
@@ -270,9 +338,15 @@ __global__ void assemble_tokens_kernel(const __nv_bfloat16* __restrict__ patch, 
 int layernorm_fwd(const float* x, int64_t ldx, const float* w, const float* b, void* y, int64_t ldy, int rows, int D,
                   float eps, cudaStream_t stream) {
   APLA_CHECK(rows > 0, "layernorm_fwd: no rows");
-  APLA_CHECK(D % 128 == 0 && D / 128 <= kMaxV4, "layernorm_fwd: D=%d must be a multiple of 128 and <= 1024", D);
+  APLA_CHECK(D > 0 && D % 4 == 0 && D <= 128 * kMaxV4, "layernorm_fwd: D=%d must be a multiple of 4 and <= 1024", D);
   APLA_CHECK(ldx % 4 == 0 && ldy % 4 == 0, "layernorm_fwd: leading dimensions must be multiples of 4");
   const int grid = cdiv(rows, 8);
+  if (D % 128 != 0) {
+    ln_fwd_generic_kernel<<<grid, 256, 0, stream>>>(x, ldx, w, b, reinterpret_cast<__nv_bfloat16*>(y), ldy, rows, D, eps);
+    APLA_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+  }
   LN_DISPATCH(D / 128, (ln_fwd_kernel<NV><<<grid, 256, 0, stream>>>(x, ldx, w, b, reinterpret_cast<__nv_bfloat16*>(y),
                                                                     ldy, rows, eps)));
   APLA_CUDA(cudaGetLastError());
@@ -284,11 +358,20 @@ int layernorm_bwd(const void* dy, int64_t ld_dy, const float* x, int64_t ldx, co
                   int64_t ld_dres, float* dx, int64_t ld_dx, void* dxb, int64_t ld_dxb, const float* gamma, void* sub,
                   int64_t ld_sub, const int* idx, int r, int r_pad, int rows, int D, float eps, cudaStream_t stream) {
   APLA_CHECK(rows > 0, "layernorm_bwd: no rows");
-  APLA_CHECK(D % 128 == 0 && D / 128 <= kMaxV4, "layernorm_bwd: D=%d must be a multiple of 128 and <= 1024", D);
+  APLA_CHECK(D > 0 && D % 4 == 0 && D <= 128 * kMaxV4, "layernorm_bwd: D=%d must be a multiple of 4 and <= 1024", D);
   APLA_CHECK(ld_dy % 4 == 0 && ldx % 4 == 0 && ld_dx % 4 == 0 && ld_dres % 4 == 0 && ld_dxb % 4 == 0,
              "layernorm_bwd: leading dimensions must be multiples of 4");
   APLA_CHECK(sub == nullptr || (idx != nullptr && r <= r_pad && r_pad <= ld_sub), "layernorm_bwd: bad gather arguments");
   const int grid = cdiv(rows, 8);
+  if (D % 128 != 0) {
+    ln_bwd_generic_kernel<<<grid, 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dy), ld_dy, x, ldx, w, dres, ld_dres, dx, ld_dx,
+        reinterpret_cast<__nv_bfloat16*>(dxb), ld_dxb, gamma, reinterpret_cast<__nv_bfloat16*>(sub), ld_sub, idx, r, r_pad,
+        rows, D, eps);
+    APLA_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+  }
   const size_t smem = sub ? size_t(8) * D * sizeof(float) : 0;
   LN_DISPATCH(D / 128, (ln_bwd_kernel<NV><<<grid, 256, smem, stream>>>(
                            reinterpret_cast<const __nv_bfloat16*>(dy), ld_dy, x, ldx, w, dres, ld_dres, dx, ld_dx,

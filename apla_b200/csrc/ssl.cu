@@ -484,7 +484,9 @@ koleo_nn_kernel(const float* __restrict__ xn, int n, int D, float eps, float w, 
     bidx[0] = bi;
   }
   __syncthreads();
-  const int j = bidx[0];
+  // a row holding NaN wins no comparison: fall back to a valid neighbour so that the NaN propagates through the
+  // distance (as in the reference) instead of indexing with -1
+  const int j = bidx[0] >= 0 ? bidx[0] : (i + 1) % n;
   const float* xj = base + int64_t(j) * D;
   float acc = 0.f;
   for (int k = threadIdx.x; k < D; k += blockDim.x) {

@@ -16,7 +16,7 @@ Differences from the reference, all deliberate:
   * `sinkhorn_knopp_teacher` skips the reference's first division by the total mass (it cancels in the first column
     normalisation); `int(B)` of the iBOT variant is one host read of a one-element tensor, as in the reference's `Q /= B`.
 Tested against oracle/ssl_oracle.py (itself pinned to the reference) in tests/test_ssl_gpu.py.
-STATUS: not yet run on hardware; verified on the CPU-emulated kernels (see csrc/ssl.cu, tests/test_ssl_emu.py)."""
+"""
 from __future__ import annotations
 
 from typing import List, Optional, Sequence
@@ -185,6 +185,8 @@ class iBOTPatchLoss(nn.Module):
         w = masks_weight.float().contiguous()
         if w.numel() != n:
             raise RuntimeError(f"masks_weight has {w.numel()} entries for {n} masked patches")
+        if n == 0:                      # no masked patch in the batch: the reference's sum over an empty tensor
+            return s[:0].sum() * 0.0   # (ibot_patch_loss.py:119-121); keeps the graph, zero gradient
         return _SoftCE.apply(s[:n], t[:n], None, w, 1.0 / student_masks_flat.shape[0], 1.0 / self.student_temp,
                              max(n, 1))
 
@@ -262,3 +264,6 @@ def update_teacher(student_params: Sequence[torch.Tensor], teacher_params: Seque
         raise RuntimeError("student and teacher parameter lists differ in length")
     for s, t in zip(student_params, teacher_params):
         ops.ema_update_(t.data, s.data, m)
+        # the kernel writes through a raw pointer: tell autograd (and the bf16 working-set caches of APLA_Attention /
+        # FusedAplaBlock, which key on (data_ptr, _version)) that the tensor changed
+        torch.autograd.graph.increment_version(t)

@@ -2,11 +2,7 @@
 (apla_b200/dinov2/loss.py) against oracle/ssl_oracle.py, which is pinned to the reference.  Everything is fp32; the bars
 (1e-4 forward, 1e-3 gradients unless stated) cover the fast-math exp / log of the kernels.
 
-FIRST HARDWARE RUN PENDING: these kernels were written after round 1's GPU budget had been spent, so they have been
-compiled for sm_100a and their closed forms checked on the CPU (tests/test_ssl_closed_forms.py), but they have never
-executed.  Until a run on a B200 has been looked at, every test here is a NON-STRICT xfail: a pass is reported as XPASS,
-a failure as xfailed, and neither hides or breaks the validated suites that run before this file.  Set
-APLA_B200_SSL_STRICT=1 to turn the marks off (round 2 does, first thing)."""
+Every test here is a plain (strict) GPU test: a failure fails the run."""
 import os
 
 import pytest
@@ -16,9 +12,6 @@ import torch.nn.functional as F
 from oracle import ssl_oracle as S
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
-if os.environ.get("APLA_B200_SSL_STRICT", "0") != "1":
-    pytestmark.append(pytest.mark.xfail(reason="csrc/ssl.cu has not had its first hardware run yet (round 1 GPU budget "
-                                               "spent); non-strict, see the module docstring", strict=False))
 
 DEV = "cuda"
 
@@ -253,8 +246,9 @@ def test_objective_matches_oracle_assembly():
     terms = 2 + n_local * 2
 
     def run(dev, dino, ibot, koleo, sm_d, sm_i):
-        a, b, c = (x.to(dev).requires_grad_(True) for x in (s_local, s_global, s_patch))
-        f = cls_feat.to(dev).requires_grad_(True)
+        # (fresh leaves per run: `.to("cpu")` would hand back the shared CPU tensor itself)
+        a, b, c = (x.detach().clone().to(dev).requires_grad_(True) for x in (s_local, s_global, s_patch))
+        f = cls_feat.detach().clone().to(dev).requires_grad_(True)
         t_d = sm_d(t_cls.to(dev)).view(2, B, K)
         t_i = sm_i(t_patch.to(dev).unsqueeze(0)).squeeze(0)
         total = dino(a.chunk(n_local), list(t_d)) / terms
