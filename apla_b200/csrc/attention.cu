@@ -10,6 +10,8 @@
 // the streaming tcgen05 kernels (attention_tc.cu, attention_tc_bwd.cu).  The first-generation mma.sync kernels and
 // the two-kernel sequence-resident backward that preceded the fused one were removed once the tcgen05 paths covered
 // every shape the tests exercise.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -62,6 +64,10 @@ int attn_bwd(const void* qkv, const void* out, const void* dout, const float* ls
     APLA_CUDA(cudaGetLastError());
     count_launch();
   }
+  // APLA_ATTN_BWD_V1=1 keeps the first-generation fused kernel for A/B measurements
+  static const bool v1 = [] { const char* e = getenv("APLA_ATTN_BWD_V1"); return e && atoi(e) != 0; }();
+  if (!v1 && attn_bwd2_supported(max_seqlen))
+    return attn_bwd2(qkv, dout, lse, delta, dqkv, cu_seqlens, num_seqs, max_seqlen, total_tokens, H, scale, stream);
   if (attn_fused_supported(max_seqlen))
     return attn_bwd_fused(qkv, dout, lse, delta, dqkv, cu_seqlens, num_seqs, max_seqlen, total_tokens, H, scale, stream);
   return attn_bwd_tc(qkv, dout, lse, delta, dqkv, cu_seqlens, num_seqs, max_seqlen, total_tokens, H, scale, stream);

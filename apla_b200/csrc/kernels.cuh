@@ -33,6 +33,11 @@ bool attn_fused_supported(int max_seqlen);
 int attn_bwd_fused(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
                    const int* cu_seqlens, int num_seqs, int max_seqlen, int total_tokens, int H, float scale,
                    cudaStream_t stream);
+// attention_bwd2.cu: second-generation fused backward (odd token on CUDA cores, event-driven issuer), max_seqlen <= 257
+bool attn_bwd2_supported(int max_seqlen);
+int attn_bwd2(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
+              const int* cu_seqlens, int num_seqs, int max_seqlen, int total_tokens, int H, float scale,
+              cudaStream_t stream);
 int attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
              const int* cu_seqlens, int num_seqs, int max_seqlen, int total_tokens, int H, float scale,
              cudaStream_t stream);

@@ -210,6 +210,37 @@ def test_update_teacher(n):
     assert rel(tp, td["w"]) < 1e-6 and torch.equal(sp.detach().cpu(), s)
 
 
+def test_update_teacher_refreshes_cached_weights():
+    """The EMA kernel writes the teacher through raw pointers; the bf16 working sets of APLA_Attention / FusedAplaBlock are
+    keyed on (data_ptr, _version).  After update_teacher the teacher backbone must compute with the NEW projection rows:
+    its output has to change and to equal that of a freshly built (un-cached) copy holding the same parameters."""
+    D, ops = _dinov2()
+    from apla_b200.config import AplaConfig
+    from apla_b200.hostdino import build_dino_backbone
+    from apla_b200.hostvit import VitArch
+    arch = VitArch(128, 2, 2)
+    torch.manual_seed(11)
+    student = build_dino_backbone(arch, img_size=56, patch_size=14, apla_config=AplaConfig(16))
+    inds = [b.attn.inds.clone() for b in student.blocks]
+    teacher = build_dino_backbone(arch, img_size=56, patch_size=14, apla_config=AplaConfig(16), indices=inds)
+    teacher.load_state_dict(student.state_dict())
+    with torch.no_grad():                                   # a student that has moved away from the teacher
+        for n, p in student.named_parameters():
+            if p.requires_grad:
+                p.add_(0.05 * torch.randn_like(p))
+    student, teacher = student.to(DEV), teacher.to(DEV)
+    x = gen(3, 3, 56, 56, seed=90).to(DEV)
+    with torch.no_grad():
+        before = teacher(x, is_training=True)["x_norm_clstoken"].clone()
+        D.update_teacher(list(student.parameters()), list(teacher.parameters()), 0.5)
+        after = teacher(x, is_training=True)["x_norm_clstoken"].clone()
+        fresh = build_dino_backbone(arch, img_size=56, patch_size=14, apla_config=AplaConfig(16), indices=inds)
+        fresh.load_state_dict({k: v.cpu() for k, v in teacher.state_dict().items()})
+        want = fresh.to(DEV)(x, is_training=True)["x_norm_clstoken"]
+    assert rel(after, before) > 1e-3, "teacher output did not move: stale cached weights"
+    assert rel(after, want) < 1e-5
+
+
 def test_centre_protocol_over_two_steps():
     """softmax_center_teacher applies the update left pending by the previous step (dino_clstoken_loss.py:28-31,88-98)."""
     D, ops = _dinov2()

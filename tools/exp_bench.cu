@@ -25,13 +25,17 @@ __global__ void __launch_bounds__(512, 1) bench(int nwarps, int iters, int mode,
         if (mode == 0) {
           p0 = exp2f(fmaf(v[2 * i], 0.18f, -ms));
           p1 = exp2f(fmaf(v[2 * i + 1], 0.18f, -ms));
+        } else if (mode == 2) {
+          p0 = exp2f(fmaf(v[2 * i], 0.18f, -ms));
+          p1 = exp2f(fmaf(v[2 * i + 1], 0.18f, -ms));
         } else {   // no MUFU: same FMA-pipe work only
           p0 = fmaf(v[2 * i], 0.18f, -ms);
           p1 = fmaf(v[2 * i + 1], 0.18f, -ms);
         }
         rs0 += p0;
         rs1 += p1;
-        acc ^= pack_bf16(p0, p1);
+        if (mode < 2) acc ^= pack_bf16(p0, p1);                   // mode 2 / 3: ex2 / fma without the bf16x2 pack
+        else acc ^= __float_as_uint(p0) ^ __float_as_uint(p1);
       }
       ms += 1e-6f * float(acc & 1);
     }
@@ -47,13 +51,13 @@ int main() {
   cudaMalloc(&d, 8);
   cudaMalloc(&sink, 4096);
   const int iters = 2000;
-  for (int mode = 0; mode < 2; ++mode)
+  for (int mode = 0; mode < 4; ++mode)
     for (int nw : {4, 8, 16}) {
       bench<<<148, 512>>>(nw, iters, mode, d, sink);
       long long c = 0;
       if (cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
       printf("%s, %2d warps/SM: %7.1f cycles per 96-element chunk per warp; %5.2f elements/clk/SM\n",
-             mode ? "fma+add+pack only" : "fma+ex2+add+pack ", nw, double(c) / iters, 96.0 * 32 * nw * iters / double(c));
+             mode == 0 ? "fma+ex2+add+pack " : mode == 1 ? "fma+add+pack only" : mode == 2 ? "fma+ex2+add (no pack)" : "fma+add (no pack)", nw, double(c) / iters, 96.0 * 32 * nw * iters / double(c));
     }
   return 0;
 }
