@@ -530,15 +530,30 @@ attn_bwd2_kernel(const __grid_constant__ Maps maps, const __nv_bfloat16* __restr
         }
         __syncwarp();
       };
+      // dP^T may run up to two chunks ahead of dV, but a chunk AHEAD may only be issued when its operands have already
+      // landed: a Q/dO block of a later group is released by (among others) this thread's own dV of an earlier chunk, so
+      // blocking for it here could wait for itself (groups of a single chunk: 50-token crops).  The chunk dV is about to
+      // need is the oldest one in flight -- everything its operands wait for has been issued -- and may block.
+      auto operands_ready = [&](const Walk& w) {
+        bool ok = true;
+        if (w.jt == 0) ok = mbar_test(&qdo_full[w.j], (w.qpar >> w.j) & 1);
+        if (ok && w.j == 0) ok = mbar_test(&kv_full[w.ts & 1], (w.ts >> 1) & 1);
+        return __all_sync(0xffffffffu, ok) != 0;
+      };
       Walk pc, dc;
       pc.init(prob);
       dc = pc;
-      for (int i = 0; i < 2 && !pc.done(prob); ++i) {
-        wait_operands(pc);
-        issue_dp(pc);
-        pc.next_chunk(prob);
-      }
       while (!dc.done(prob)) {
+        while (!pc.done(prob) && pc.c <= dc.c) {
+          wait_operands(pc);
+          issue_dp(pc);
+          pc.next_chunk(prob);
+        }
+        if (!pc.done(prob) && pc.c - dc.c < 2 && operands_ready(pc)) {
+          tc_fence_after();
+          issue_dp(pc);
+          pc.next_chunk(prob);
+        }
         const int slot = dc.ts & 1;
         WAIT(&pd_full[dc.c & 1], (dc.c >> 1) & 1, 8);
         if (dc.j == 0) WAIT(acc_empty, (dc.ts & 1) ^ 1, 9);
@@ -559,8 +574,9 @@ attn_bwd2_kernel(const __grid_constant__ Maps maps, const __nv_bfloat16* __restr
         }
         __syncwarp();
         dc.next_chunk(prob);
-        if (!pc.done(prob)) {
-          wait_operands(pc);
+        // dP^T of the chunk two ahead goes right behind this dV (same TMEM slot) if its operands are there already
+        while (!pc.done(prob) && pc.c - dc.c < 2 && operands_ready(pc)) {
+          tc_fence_after();
           issue_dp(pc);
           pc.next_chunk(prob);
         }

@@ -285,11 +285,15 @@ def test_attention_cls_only(B, N, H):
     assert float(dqkv[mask][:, :D].float().abs().max()) == 0.0                          # dQ of non-CLS rows: exact zeros
 
 
-def test_attention_varlen():
+@pytest.mark.parametrize("H,seqlens", [(4, [257, 50, 257, 50, 50, 3, 130]),
+                                       # the DINOv2 multi-crop pattern: global crops, then MANY single-chunk local crops per
+                                       # CTA (the second-generation backward once deadlocked on exactly this)
+                                       (16, [257] * 6 + [50] * 90),
+                                       (2, [257, 65, 256, 1, 129, 64, 257, 257, 200, 193] * 16)])
+def test_attention_varlen(H, seqlens):
     ops = _cuda()
     g = torch.Generator(device="cuda").manual_seed(5)
-    H, D = 4, 256
-    seqlens = [257, 50, 257, 50, 50, 3, 130]
+    D = H * 64
     T = sum(seqlens)
     cu = torch.tensor([0] + list(torch.tensor(seqlens).cumsum(0)), dtype=torch.int32, device="cuda")
     qkv = bf(torch.randn(T, 3 * D, device="cuda", generator=g))

@@ -69,10 +69,11 @@ def main():
         ok &= check([64] * 2, 2, True)
         ok &= check([17] * 5, 2, True)
         ok &= check([272] * 2, 2, True)
-        for n in (65, 128, 129, 193, 256, 1, 63):          # odd-token edge cases of the second-generation backward
+        for n in (65, 128, 129, 193, 256, 63):          # odd-token edge cases of the second-generation backward
             ok &= check([n] * 3, 2, True, seed=n)
         ok &= check([257] * 300, 3, True, seed=9)           # several groups per CTA
         ok &= check([257, 65, 256, 1, 129, 64, 257, 257, 200, 193], 2, False, seed=4)
+        ok &= check([257] * 6 + [50] * 90, 16, False, seed=6)   # multi-crop: many single-chunk groups per CTA
         ok &= check([257] * 30, 12, True, seed=3)
         ok &= check([257, 50, 257, 50, 50, 3, 130], 4, False)
         ok &= check([1370], 12, True)
