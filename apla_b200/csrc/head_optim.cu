@@ -106,6 +106,12 @@ head_dgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ W
 // ------------------------------------------------------------------------------------------------
 // optimiser tail over the arena
 // ------------------------------------------------------------------------------------------------
+// Deterministic: every block leaves its partial sum in ws[block]; the block that finishes last adds the partials in
+// index order.  (An atomicAdd of the partials gave a run-to-run different last bit, hence a different clip coefficient
+// on every data-parallel rank: the ranks' parameters drifted apart by an ulp per step -- found by tools/dp_check.py.)
+// out[0] = result, out[1 .. kSumsqBlocks] = partials, out[kSumsqBlocks + 1] = arrival counter (reset by the last block).
+constexpr int kSumsqBlocks = 592;
+static_assert(kSumsqBlocks + 2 <= 600, "APLA_SUMSQ_FLOATS (include/apla_b200.h) must cover result + partials + counter");
 __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float scale, float* __restrict__ out) {
   float acc = 0.f;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
@@ -114,12 +120,36 @@ __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float scale
   }
   acc = warp_sum(acc);
   __shared__ float red[32];
+  __shared__ bool last;
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x < 32) {
     float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
     v = warp_sum(v);
-    if (threadIdx.x == 0) atomicAdd(out, v);
+    if (threadIdx.x == 0) {
+      out[1 + blockIdx.x] = v;
+      __threadfence();
+      unsigned* counter = reinterpret_cast<unsigned*>(out + 1 + kSumsqBlocks);
+      last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // fixed order: thread t sums partials t, t + 256, ... ; then the same warp / block tree as above
+  float v = 0.f;
+  for (int i = threadIdx.x; i < int(gridDim.x); i += blockDim.x) v += __ldcg(out + 1 + i);
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) {
+      out[0] = t;
+      *reinterpret_cast<unsigned*>(out + 1 + kSumsqBlocks) = 0u;   // ready for the next launch (also under graph replay)
+    }
   }
 }
 
@@ -207,8 +237,9 @@ int head_bwd(const float* dlogits, const void* xn, const float* W, float* dW, fl
 
 int grad_sumsq(const float* g, int64_t n, float scale, float* out, cudaStream_t s) {
   APLA_CHECK(n > 0, "grad_sumsq: empty");
-  APLA_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
-  const int grid = (int)((n + 1023) / 1024 < 592 ? (n + 1023) / 1024 : 592);
+  // `out` holds APLA_SUMSQ_FLOATS floats (include/apla_b200.h): result, per-block partials, arrival counter.  The counter
+  // is zero on entry: the caller zero-initialises the buffer once and every launch leaves it at zero.
+  const int grid = (int)((n + 1023) / 1024 < kSumsqBlocks ? (n + 1023) / 1024 : kSumsqBlocks);
   sumsq_kernel<<<grid, 256, 0, s>>>(g, n, scale, out);
   APLA_CUDA(cudaGetLastError());
   count_launch();

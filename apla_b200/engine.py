@@ -137,7 +137,7 @@ class FineTuneEngine:
         self.grads = self._new(n, dtype=F32, zero=True)
         self.exp_avg = self._new(n, dtype=F32, zero=True)
         self.exp_avg_sq = self._new(n, dtype=F32, zero=True)
-        self.sumsq = self._new(1, dtype=F32, zero=True)
+        self.sumsq = self._new(600, dtype=F32, zero=True)      # APLA_SUMSQ_FLOATS: [0] = result, rest scratch
         o_w1, o_fcw = 0, L * r * D
         o_b1 = o_fcw + C * D
         o_fcb = o_b1 + L * r
@@ -571,4 +571,4 @@ class FineTuneEngine:
 
     def grad_norm(self) -> torch.Tensor:
         """sqrt of the sum of squares the last optim_step clipped with (after the 1/world scaling)."""
-        return self.sumsq.sqrt()
+        return self.sumsq[:1].sqrt()

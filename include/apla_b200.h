@@ -138,7 +138,10 @@ int apla_head_bwd(const float* dlogits, const void* xn, const float* W, float* d
                   int C, apla_stream_t stream);
 
 /* --- optimiser tail over one contiguous fp32 arena -------------------------------------------------------- */
-/* *out = sum (scale*g)^2 */
+/* out[0] = sum (scale*g)^2, bit-reproducible (fixed summation order: every data-parallel rank must derive the same clip
+ * coefficient from the same all-reduced gradients).  `out` is a ZERO-INITIALISED buffer of APLA_SUMSQ_FLOATS floats owned by
+ * the caller: out[0] is the result, the rest is scratch that every call leaves zeroed. */
+#define APLA_SUMSQ_FLOATS 600
 int apla_grad_sumsq(const float* g, int64_t n, float scale, float* out, apla_stream_t stream);
 /* clip_grad_norm_(max_norm) (trainer.py:136) + torch.optim.AdamW step (wrappers.py:199-221): elements
  * [0,n_decay) are decayed.  gscale pre-multiplies the gradients (1/world for the DDP mean). */

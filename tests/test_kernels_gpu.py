@@ -316,7 +316,7 @@ def test_clip_adamw_arena_matches_torch():
     n, n_decay = 100_003, 90_000
     p0 = torch.randn(n, device="cuda", generator=g) * 0.02
     ours = p0.clone(); m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
-    ss = torch.zeros(1, device="cuda")
+    ss = torch.zeros(600, device="cuda")                      # APLA_SUMSQ_FLOATS: [0] result, rest scratch
     pa = torch.nn.Parameter(p0[:n_decay].clone()); pb = torch.nn.Parameter(p0[n_decay:].clone())
     opt = torch.optim.AdamW([{"params": [pa]}, {"params": [pb], "weight_decay": 0.0}], lr=3e-5, weight_decay=1e-5)
     for step in range(1, 4):
@@ -328,7 +328,8 @@ def test_clip_adamw_arena_matches_torch():
         pa.grad = grad[:n_decay] / world; pb.grad = grad[n_decay:] / world
         gn = torch.nn.utils.clip_grad_norm_([pa, pb], 1.0)
         opt.step()
-        assert abs(float(ss.sqrt()) - float(gn)) <= 1e-5 * float(gn)
+        assert abs(float(ss[0].sqrt()) - float(gn)) <= 1e-5 * float(gn)
+        assert float(ss[1:].abs().max()) >= 0.0 and int(ss[593:].view(torch.int32)[0]) == 0   # counter back at zero
         ref = torch.cat([pa.detach(), pb.detach()])
         assert rel(ours - p0, ref - p0) < 1e-4
         assert rel(ours, ref) < 1e-6

@@ -55,6 +55,11 @@ def main():
         ref.forward(xa, ya); ref.backward()
         torch.cuda.synchronize()
         g_dp = eng.grads / world
+        gg = [torch.empty_like(eng.grads) for _ in range(world)]
+        dist.all_gather(gg, eng.grads)
+        o = eng.offsets
+        regions = dict(w1=(o["w1"], o["fcw"]), fcw=(o["fcw"], o["b1"]), b1=(o["b1"], o["fcb"]), fcb=(o["fcb"], o["n"]))
+        grad_diff = {k: float((gg[0][a:b] - gg[-1][a:b]).abs().max()) for k, (a, b) in regions.items()}
         e_grad = rel(g_dp, ref.grads)
         cos = float(torch.nn.functional.cosine_similarity(g_dp.double(), ref.grads.double(), dim=0))
         eng.optim_step(); ref.optim_step()
@@ -68,9 +73,15 @@ def main():
         gathered = [torch.empty_like(sig) for _ in range(world)]
         dist.all_gather(gathered, sig)
         identical = all(torch.equal(gathered[0], t) for t in gathered)
+        n = eng.n_arena
+        param_diff = {k: float((gathered[0][a:b] - gathered[-1][a:b]).abs().max()) for k, (a, b) in regions.items()}
+        half = eng.shape["L"] // 2 * eng.shape["r"] * eng.shape["D"]
+        param_diff["w1_lower_half"] = float((gathered[0][:half] - gathered[-1][:half]).abs().max())
+        param_diff["w1_upper_half"] = float((gathered[0][half:o["fcw"]] - gathered[-1][half:o["fcw"]]).abs().max())
         moved = rel(eng.params, make(B, solo[rank]).params)       # how far training moved the parameters (sanity)
         results[f"r{r_apla}_{'graph' if use_graph else 'eager'}"] = dict(
-            grad_rel=e_grad, grad_cosine=cos, params_rel_after_steps=e_param, identical_across_ranks=identical,
+            grad_rel=e_grad, grad_cosine=cos, grad_max_diff_between_ranks_step1=grad_diff,
+            param_max_diff_between_ranks=param_diff, params_rel_after_steps=e_param, identical_across_ranks=identical,
             params_moved_rel=moved)
         ok &= identical and e_grad < 1e-2 and cos > 0.9999 and e_param < 1e-3 and moved > 1e-4
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
