@@ -450,18 +450,19 @@ attn_fwd_sr_kernel(const __grid_constant__ Maps maps, const __nv_bfloat16* __res
     reg_dealloc<80>();
     // Query rows 256.. of a 257/258-token sequence on CUDA cores (4 warps, fp32): scores against the resident K,
     // softmax, P.V against the resident V.  The helpers also take part in releasing every group's K/V buffer.
+    // (explicit ld.shared / st.shared by 32-bit address: the pointer arithmetic on the aligned dynamic buffer otherwise
+    //  compiles to generic LD / ST, which take the slow local/global path -- see ptx.cuh)
     const int e = threadIdx.x - 384, hw = warp - 12;
-    float* hp = reinterpret_cast<float*>(smem + OFF_HELP);
-    float* hpart = hp + 384;
-    float* hred = hpart + 256;
+    const uint32_t sb = smem_u32(smem);
+    const uint32_t hp = sb + OFF_HELP, hpart = hp + 384 * 4, hred = hpart + 256 * 4;
     const float sl2 = scale * LOG2E;
     Walk k;
     k.init(prob);
     while (!k.done(prob)) {
       const int gb = k.gi & 1;
       mbar_wait(&kv_full[gb], (k.gi >> 1) & 1);
-      const uint8_t* sK = smem + OFF_KV + gb * 2 * RES_BYTES;
-      const uint8_t* sV = sK + RES_BYTES;
+      const uint32_t sK = sb + OFF_KV + gb * 2 * RES_BYTES;
+      const uint32_t sV = sK + RES_BYTES;
       for (int r = 0; r < k.simt_rows; ++r) {
         const int T = 256 + r;
         const uint4* qg = reinterpret_cast<const uint4*>(qkv + size_t(k.row_start + T) * (3 * D) + k.h * 64);
@@ -475,11 +476,11 @@ attn_fwd_sr_kernel(const __grid_constant__ Maps maps, const __nv_bfloat16* __res
           const int key = e + 128 * i;
           sc[i] = -INFINITY;
           if (key < k.n) {
-            const uint8_t* kr = sK + key * 128;
+            const uint32_t kr = sK + key * 128;
             float a0 = 0.f, a1 = 0.f;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-              const uint4 kv = *reinterpret_cast<const uint4*>(kr + ((u ^ (key & 7)) << 4));
+              const uint4 kv = lds_u4(kr + ((u ^ (key & 7)) << 4));
               const uint32_t kw[4] = {kv.x, kv.y, kv.z, kv.w}, qw[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
 #pragma unroll
               for (int x = 0; x < 4; ++x) {
@@ -493,36 +494,42 @@ attn_fwd_sr_kernel(const __grid_constant__ Maps maps, const __nv_bfloat16* __res
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (lane == 0) hred[hw] = mx;
+        if (lane == 0) sts_f32(hred + hw * 4, mx);
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        mx = fmaxf(fmaxf(hred[0], hred[1]), fmaxf(hred[2], hred[3]));
+        {
+          const float4 m4 = lds_f4(hred);
+          mx = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w));
+        }
         float sum = 0.f;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           const int key = e + 128 * i;
           const float pv = key < k.n ? exp2f((sc[i] - mx) * sl2) : 0.f;
-          hp[key] = pv;
+          if (key < 384) sts_f32(hp + key * 4, pv);
           sum += pv;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (lane == 0) hred[4 + hw] = sum;
+        if (lane == 0) sts_f32(hred + (4 + hw) * 4, sum);
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        const float l = (hred[4] + hred[5]) + (hred[6] + hred[7]);
+        const float4 l4 = lds_f4(hred + 16);
+        const float l = (l4.x + l4.y) + (l4.z + l4.w);
         // O[T, 2 dp .. 2 dp + 1] over the keys part, part + 4, ...
         const int dp = e & 31, part = e >> 5;
         float o0 = 0.f, o1 = 0.f;
+#pragma unroll 4
         for (int key = part; key < k.n; key += 4) {
-          const float pv = hp[key];
-          const uint32_t vv = *reinterpret_cast<const uint32_t*>(sV + key * 128 + (((dp >> 2) ^ (key & 7)) << 4) + (dp & 3) * 4);
+          const float pv = lds_f32(hp + key * 4);
+          const uint32_t vv = lds_u32(sV + key * 128 + (((dp >> 2) ^ (key & 7)) << 4) + (dp & 3) * 4);
           o0 = fmaf(pv, bf16_lo(vv), o0);
           o1 = fmaf(pv, bf16_hi(vv), o1);
         }
-        hpart[part * 64 + 2 * dp] = o0;
-        hpart[part * 64 + 2 * dp + 1] = o1;
+        sts_f32(hpart + (part * 64 + 2 * dp) * 4, o0);
+        sts_f32(hpart + (part * 64 + 2 * dp + 1) * 4, o1);
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (e < 64) {
-          const float o = (hpart[e] + hpart[64 + e]) + (hpart[128 + e] + hpart[192 + e]);
+          const float o = (lds_f32(hpart + e * 4) + lds_f32(hpart + (64 + e) * 4)) +
+                          (lds_f32(hpart + (128 + e) * 4) + lds_f32(hpart + (192 + e) * 4));
           out[size_t(k.row_start + T) * D + k.h * 64 + e] = __float2bfloat16_rn(o / l);
         }
         if (e == 0) lse[size_t(k.row_start + T) * H + k.h] = mx * scale + logf(l);
