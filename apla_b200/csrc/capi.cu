@@ -223,4 +223,19 @@ int apla_ssl_objective(const float* s_scores, int64_t lds, const float* t_scores
                        ds_is_bf16, gscale, losses, dino_batch_sum, ibot_batch_mean, S(stream));
 }
 
+int apla_grad_arena_allreduce(const void* const* peer_bufs, const void* const* peer_flags, void* multicast, void* epochs,
+                              int rank, int world, int64_t offset_floats, int64_t count_floats, int64_t offset_b,
+                              int64_t count_b, int channel, int ctas, apla_stream_t stream) {
+  if (!peer_bufs || !peer_flags || !epochs) {
+    set_error("apla_grad_arena_allreduce: null argument");
+    return 1;
+  }
+  return grad_arena_allreduce(reinterpret_cast<float* const*>(const_cast<void* const*>(peer_bufs)),
+                              reinterpret_cast<uint32_t* const*>(const_cast<void* const*>(peer_flags)),
+                              reinterpret_cast<float*>(multicast), reinterpret_cast<uint32_t*>(epochs), rank, world,
+                              offset_floats, count_floats, offset_b, count_b, channel, ctas, S(stream));
+}
+int apla_grad_arena_allreduce_flag_words(void) { return grad_arena_allreduce_flag_words(); }
+int apla_grad_arena_allreduce_epoch_words(void) { return grad_arena_allreduce_epoch_words(); }
+
 }  // extern "C"

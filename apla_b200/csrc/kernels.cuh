@@ -75,6 +75,13 @@ int adamw_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t 
 int proj_refresh(const float* w1, const float* b1, const int* idx, void* wfull, void* wfullT, float* bfull, int L,
                  int r, int D, int64_t w1_block_stride, int64_t b1_block_stride, cudaStream_t s);
 
+// dp_allreduce.cu: two-shot all-reduce of the gradient arena over symmetric (peer-mapped) memory, graph-capturable
+int grad_arena_allreduce(float* const* peer_bufs, uint32_t* const* peer_flags, float* multicast, uint32_t* epochs, int rank,
+                         int world, int64_t offset_floats, int64_t count_floats, int64_t offset_b, int64_t count_b,
+                         int channel, int ctas, cudaStream_t stream);
+int grad_arena_allreduce_flag_words();
+int grad_arena_allreduce_epoch_words();
+
 // ssl.cu: row kernels of the DINOv2 self-supervised objective
 int ssl_softmax_center(const float* t, int64_t ldt, const float* center, float inv_temp, int rows, int K, float* out,
                        int64_t ldo, cudaStream_t s);

@@ -134,7 +134,22 @@ class FineTuneEngine:
         n = LIB.load().apla_engine_arena_size(self._handle)
         self.n_arena = int(n)
         self.params = self._new(n, dtype=F32, zero=True)
-        self.grads = self._new(n, dtype=F32, zero=True)
+        # data parallel: the gradient arena lives in symmetric (peer-mapped) memory and is reduced by the library's own
+        # kernel (apla_grad_arena_allreduce), which -- unlike an NCCL call -- is captured in the step's CUDA graph
+        self._peer = None
+        if self.world > 1:
+            from .dp import make_peer_arena
+            self._peer = make_peer_arena(n, self.device, self.pg)
+            # every rank must take the same path: if symmetric memory failed anywhere, all ranks use NCCL
+            ok = torch.tensor([1 if self._peer is not None else 0], device=self.device)
+            torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN, group=self.pg)
+            if int(ok.item()) == 0:
+                self._peer = None
+        if self._peer is not None:
+            self.grads = self._peer.grads()
+            self._keep.append(self._peer.buf)
+        else:
+            self.grads = self._new(n, dtype=F32, zero=True)
         self.exp_avg = self._new(n, dtype=F32, zero=True)
         self.exp_avg_sq = self._new(n, dtype=F32, zero=True)
         self.sumsq = self._new(600, dtype=F32, zero=True)      # APLA_SUMSQ_FLOATS: [0] = result, rest scratch
@@ -392,19 +407,27 @@ class FineTuneEngine:
         lay = ArenaLayout(L=L, r=self.shape["r"], D=self.shape["D"], C=self.shape["C"])
         half = lay.split_block()
         cur = torch.cuda.current_stream()
+
+        def reduce(which):
+            if self._peer is not None:
+                # few CTAs while the lower backward shares the GPU, more for the exposed tail
+                self._peer.all_reduce_chunks(lay, which, ctas=32 if which == "early" else 96)
+            else:
+                allreduce_arena(self.grads, lay, group=self.pg, which=which)
+
         LIB.call("apla_engine_backward", self._handle, L - 1, half, stream())
         ev = torch.cuda.Event()
         ev.record(cur)
         with torch.cuda.stream(self._ar_stream):
             self._ar_stream.wait_event(ev)
-            allreduce_arena(self.grads, lay, group=self.pg, which="early")
+            reduce("early")
         if half > 0:
             LIB.call("apla_engine_backward", self._handle, half - 1, 0, stream())
         ev2 = torch.cuda.Event()
         ev2.record(cur)
         with torch.cuda.stream(self._ar_stream):
             self._ar_stream.wait_event(ev2)
-            allreduce_arena(self.grads, lay, group=self.pg, which="late")
+            reduce("late")
         cur.wait_stream(self._ar_stream)
 
     def reset_graphs(self):
@@ -473,6 +496,14 @@ class FineTuneEngine:
                     LIB.call("apla_engine_backward", self._handle, L - 1, 0, stream())
                     optim()
                 g = (capture(whole),)
+            elif self._peer is not None:
+                # data parallel with the native all-reduce: ONE graph; the early slice's reduction is forked onto the
+                # side stream inside the capture and joins before the optimiser
+                def whole_dp():
+                    LIB.call("apla_engine_forward", self._handle, ptr(images), ptr(labels), inv_b, inv_b, stream())
+                    self.backward()
+                    optim()
+                g = (capture(whole_dp),)
             else:
                 from .dp import ArenaLayout
                 half = ArenaLayout(L=L, r=self.shape["r"], D=self.shape["D"], C=self.shape["C"]).split_block()
@@ -488,7 +519,7 @@ class FineTuneEngine:
             self._graph_keep = getattr(self, "_graph_keep", []) + [(images, labels)]   # keep the buffers alive
         self.step_count += 1
         self._push_hyper()
-        if self.world == 1:
+        if self.world == 1 or self._peer is not None:
             g[0].replay()
             return self.loss
         from .dp import ArenaLayout, allreduce_arena

@@ -513,11 +513,19 @@ def run_ssl(args):
     batch_host = ssl_batch(B, w, seed=1234 + rank)
     batch_pin = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in batch_host.items()}
     batch_dev = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch_host.items()}
-    flat = None
+    flat = peer = None
     if world > 1:
         # the reference wraps the student in DDP (dinov2/wrappers.py:76-77); here the trainable gradients are reduced as
-        # ONE flat buffer after backward (mean), which is what DDP's buckets amount to for ~27 M parameters
-        flat = torch.zeros(sum(p.numel() for p in trainable), device=dev)
+        # ONE flat buffer after backward (mean) -- by the library's own NVLink all-reduce kernel over symmetric memory
+        # (apla_grad_arena_allreduce; 49 M parameters = 195 MB), NCCL if symmetric memory is unavailable
+        from apla_b200.dp import make_peer_arena
+        n_flat = sum(p.numel() for p in trainable)
+        peer = make_peer_arena(n_flat, dev)
+        ok = torch.tensor([1 if peer is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            peer = None
+        flat = peer.grads() if peer is not None else torch.zeros(n_flat, device=dev)
 
     def step(batch):
         opt.zero_grad(set_to_none=True)
@@ -525,7 +533,10 @@ def run_ssl(args):
         loss.backward()
         if world > 1:
             torch.cat([p.grad.reshape(-1) for p in trainable], out=flat)
-            dist.all_reduce(flat)
+            if peer is not None:
+                peer.all_reduce(0, flat.numel(), 0, ctas=64)
+            else:
+                dist.all_reduce(flat)
             flat.mul_(1.0 / world)
             o = 0
             for p in trainable:
@@ -579,6 +590,7 @@ def run_ssl(args):
             e2e=dict(value=B * world / (ms_e2e * 1e-3), unit="images/s", ms_per_step=ms_e2e, h2d_bytes_per_step=h2d,
                      d2h_bytes_per_step=4),
             objective="per-term loss classes" if args.per_term_losses else "fused head + apla_ssl_objective",
+            grad_allreduce=("native apla_grad_arena_allreduce" if peer is not None else "nccl") if world > 1 else None,
             masked_patches=int(batch_host["mask_indices_list"].shape[0]),
             trainable_params=sum(p.numel() for p in trainable), peak_hbm_gb=round(torch.cuda.max_memory_allocated() / 1e9, 1),
             gpu_launches=launches_per_step * args.steps, gpu_launches_per_step=launches_per_step, clocks=clocks)

@@ -299,6 +299,23 @@ int apla_engine_backward(apla_engine_t e, int block_from, int block_to, apla_str
 int apla_engine_optim(apla_engine_t e, float gscale, float max_norm, float lr, float wd, float beta1, float beta2,
                       float eps, int step, apla_stream_t stream);
 
+/* --- data-parallel gradient exchange -------------------------------------------------------------------- */
+/* In-place sum all-reduce of arena[offset, offset + count) across the `world` GPUs of one node, as ONE kernel launch
+ * (capturable in a CUDA graph): replaces the DDP reducer's NCCL all-reduce of the trainable gradients
+ * (src/defaults/wrappers.py:182-183; SURVEY.md 8b `apla_grad_arena_allreduce`).  peer_bufs[i] / peer_flags[i] are HOST
+ * arrays of DEVICE pointers to rank i's arena and flag words as mapped into THIS process (symmetric / peer memory);
+ * flags hold apla_grad_arena_allreduce_flag_words() zero-initialised uint32 per rank; `epochs` is a LOCAL zero-initialised
+ * device buffer of apla_grad_arena_allreduce_epoch_words() uint32.  offset and count are multiples of 4 floats.
+ * A second slice [offset_b, offset_b + count_b) (count_b may be 0) is reduced by the same launch.  `multicast` is the
+ * NVLS multicast mapping of the arena (NULL: plain peer loads / stores).
+ * Every rank must issue the same sequence of calls per channel (0..3); calls on different channels may overlap.
+ * The result is bit-identical on all ranks (one owner per element). `ctas` <= 148 (0 = 32), 128 threads each. */
+int apla_grad_arena_allreduce(const void* const* peer_bufs, const void* const* peer_flags, void* multicast, void* epochs,
+                              int rank, int world, int64_t offset_floats, int64_t count_floats, int64_t offset_b,
+                              int64_t count_b, int channel, int ctas, apla_stream_t stream);
+int apla_grad_arena_allreduce_flag_words(void);
+int apla_grad_arena_allreduce_epoch_words(void);
+
 #ifdef __cplusplus
 }
 #endif
