@@ -241,8 +241,9 @@ for _name in sorted(dir(G)):
     _fn = getattr(G, _name)
     if not _name.startswith("test_") or not callable(_fn):
         continue
-    if _name == "test_ssl_step_against_reference_vectors":      # needs the real fused backbone; its CPU counterpart is
-        continue                                                # test_meta_arch_two_steps_against_reference_vectors
+    if _name in ("test_ssl_step_against_reference_vectors",     # needs the real fused backbone; its CPU counterpart is
+                 "test_update_teacher_refreshes_cached_weights"):   # test_meta_arch_two_steps_against_reference_vectors;
+        continue                                                # the second checks caches that live in the CUDA modules
     _params = [m for m in getattr(_fn, "pytestmark", []) if m.name == "parametrize"]
     if not _params:
         CASES.append(pytest.param(_name, {}, id=_name))
