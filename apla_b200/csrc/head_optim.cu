@@ -103,6 +103,102 @@ head_dgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ W
     dxn[size_t(b) * D + d] = __float2bfloat16_rn((red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]));
 }
 
+// ---- second-generation head kernels: the first ones re-read the whole weight matrix per image (109 MB of L2 traffic for
+// a 27 MFLOP product) and took 36 + 50 us of an 8.2 ms step; these keep the reused operand in shared memory: 9.5 + ~20 us.
+// (A one-warp-per-class forward with the weight row in registers was 10x SLOWER than head_fwd_kernel -- four warps per SM
+// cannot hide the load latency -- and was dropped.)
+
+// dW tile of 32 classes x 64 features per block, the two operand tiles of 64 images staged in shared memory
+__global__ void __launch_bounds__(256)
+head_wgrad2_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ xn, float* __restrict__ dW,
+                   float* __restrict__ db, int B, int D, int C) {
+  __shared__ float sdl[64][32];
+  __shared__ __align__(16) float sxn[64][64];
+  const int c_tile = blockIdx.x * 32, d_tile = blockIdx.y * 64;
+  const int tc = threadIdx.x >> 4, td = threadIdx.x & 15;       // 2 classes x 4 features per thread
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float accb[2] = {0.f, 0.f};
+  for (int b0 = 0; b0 < B; b0 += 64) {
+    for (int i = threadIdx.x; i < 64 * 32; i += 256) {
+      const int b = i >> 5, c = i & 31;
+      sdl[b][c] = (b0 + b < B && c_tile + c < C) ? __ldg(dlogits + size_t(b0 + b) * C + c_tile + c) : 0.f;
+    }
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+      const int b = i >> 6, d = i & 63;
+      sxn[b][d] = (b0 + b < B && d_tile + d < D) ? __bfloat162float(xn[size_t(b0 + b) * D + d_tile + d]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int b = 0; b < 64; ++b) {
+      const float g0 = sdl[b][2 * tc], g1 = sdl[b][2 * tc + 1];
+      const float4 x = *reinterpret_cast<const float4*>(&sxn[b][4 * td]);
+      acc[0][0] = fmaf(g0, x.x, acc[0][0]); acc[0][1] = fmaf(g0, x.y, acc[0][1]);
+      acc[0][2] = fmaf(g0, x.z, acc[0][2]); acc[0][3] = fmaf(g0, x.w, acc[0][3]);
+      acc[1][0] = fmaf(g1, x.x, acc[1][0]); acc[1][1] = fmaf(g1, x.y, acc[1][1]);
+      acc[1][2] = fmaf(g1, x.z, acc[1][2]); acc[1][3] = fmaf(g1, x.w, acc[1][3]);
+      accb[0] += g0;
+      accb[1] += g1;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = c_tile + 2 * tc + i;
+    if (c >= C) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = d_tile + 4 * td + j;
+      if (d < D) dW[size_t(c) * D + d] = acc[i][j];
+    }
+    if (blockIdx.y == 0 && td == 0) db[c] = accb[i];
+  }
+}
+
+// dxn for IMG images per block: the images' dlogits rows sit in shared memory, a weight element is loaded once per IMG uses
+constexpr int kHeadImg = 4;
+__global__ void __launch_bounds__(256)
+head_dgrad2_kernel(const float* __restrict__ dlogits, const float* __restrict__ W, __nv_bfloat16* __restrict__ dxn, int B,
+                   int D, int C) {
+  extern __shared__ float sdl2[];                 // [kHeadImg][C], then the reduction scratch [4][kHeadImg][64]
+  float* red = sdl2 + kHeadImg * C;
+  const int b0 = blockIdx.y * kHeadImg, col = threadIdx.x & 63, d = blockIdx.x * 64 + col, part = threadIdx.x >> 6;
+  for (int i = threadIdx.x; i < kHeadImg * C; i += 256) {
+    const int b = i / C, c = i - b * C;
+    sdl2[i] = b0 + b < B ? __ldg(dlogits + size_t(b0 + b) * C + c) : 0.f;
+  }
+  __syncthreads();
+  float acc[kHeadImg];
+#pragma unroll
+  for (int i = 0; i < kHeadImg; ++i) acc[i] = 0.f;
+  if (d < D) {
+    int c = part;
+    for (; c + 12 < C; c += 16) {                 // four independent weight loads in flight
+      float w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) w[u] = __ldg(W + size_t(c + 4 * u) * D + d);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < kHeadImg; ++i) acc[i] = fmaf(sdl2[i * C + c + 4 * u], w[u], acc[i]);
+    }
+    for (; c < C; c += 4) {
+      const float w = __ldg(W + size_t(c) * D + d);
+#pragma unroll
+      for (int i = 0; i < kHeadImg; ++i) acc[i] = fmaf(sdl2[i * C + c], w, acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kHeadImg; ++i) red[(part * kHeadImg + i) * 64 + col] = acc[i];
+  __syncthreads();
+  if (part == 0 && d < D) {
+#pragma unroll
+    for (int i = 0; i < kHeadImg; ++i)
+      if (b0 + i < B)
+        dxn[size_t(b0 + i) * D + d] = __float2bfloat16_rn((red[i * 64 + col] + red[(kHeadImg + i) * 64 + col]) +
+                                                          (red[(2 * kHeadImg + i) * 64 + col] + red[(3 * kHeadImg + i) * 64 + col]));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // optimiser tail over the arena
 // ------------------------------------------------------------------------------------------------
@@ -226,10 +322,17 @@ int cross_entropy(const float* logits, const int64_t* labels, float* dlogits, fl
 int head_bwd(const float* dlogits, const void* xn, const float* W, float* dW, float* db, void* dxn, int B, int D, int C,
              cudaStream_t s) {
   APLA_CHECK(B > 0 && D > 0 && C > 0, "head_bwd: empty");
-  head_wgrad_kernel<<<cdiv(C * D, 256), 256, 0, s>>>(dlogits, reinterpret_cast<const __nv_bfloat16*>(xn), dW, db, B, D, C);
+  head_wgrad2_kernel<<<dim3(cdiv(C, 32), cdiv(D, 64)), 256, 0, s>>>(dlogits, reinterpret_cast<const __nv_bfloat16*>(xn), dW, db,
+                                                                    B, D, C);
   APLA_CUDA(cudaGetLastError());
   count_launch();
-  head_dgrad_kernel<<<dim3(cdiv(D, 64), B), 256, 0, s>>>(dlogits, W, reinterpret_cast<__nv_bfloat16*>(dxn), B, D, C);
+  const size_t smem = (size_t(kHeadImg) * C + 4 * kHeadImg * 64) * sizeof(float);
+  if (smem <= 48 * 1024) {
+    head_dgrad2_kernel<<<dim3(cdiv(D, 64), cdiv(B, kHeadImg)), 256, smem, s>>>(dlogits, W, reinterpret_cast<__nv_bfloat16*>(dxn),
+                                                                               B, D, C);
+  } else {   // very wide heads: the per-image kernel
+    head_dgrad_kernel<<<dim3(cdiv(D, 64), B), 256, 0, s>>>(dlogits, W, reinterpret_cast<__nv_bfloat16*>(dxn), B, D, C);
+  }
   APLA_CUDA(cudaGetLastError());
   count_launch();
   return 0;
