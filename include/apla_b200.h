@@ -155,7 +155,7 @@ int apla_proj_refresh(const float* w1, const float* b1, const int32_t* idx, void
 /* --- DINOv2 self-supervised objective: HBM-bound row kernels (BASELINE config C4) ------- */
 /* Paths below are relative to src/self_supervised/dinov2/.  K = number of prototypes (65 536 in the shipped configs),
  * K % 4 == 0, rows 16-byte aligned.  All tensors f32 unless a name says bf16.  Reductions are fixed-order.
- * STATUS: built for sm_100a, first hardware run scheduled for round 2 (tests/test_ssl_gpu.py). */
+ * Validated on the B200 against oracle/ssl_oracle.py (tests/test_ssl_gpu.py, strict). */
 /* out[rows,K] = softmax((t - center[K]) * inv_temp): DINOLoss.softmax_center_teacher loss/dino_clstoken_loss.py:28-31,
  * iBOTPatchLoss.softmax_center_teacher loss/ibot_patch_loss.py:39-51. */
 int apla_softmax_center(const float* t, int64_t ldt, const float* center, float inv_temp, int rows, int K, float* out,

@@ -18,7 +18,7 @@ def golden_dir():
     return GOLDEN
 
 
-# A kernel that faults on its first hardware run (tests/test_ssl_gpu.py, non-strict xfails) leaves a STICKY CUDA error: the
+# A kernel that faults (e.g. a new tcgen05 kernel on its first hardware run) leaves a STICKY CUDA error: the
 # tests after it fail fast, the summary is printed -- and then torch's teardown of the broken context can abort the
 # interpreter, replacing pytest's exit status with SIGABRT.  If (and only if) the context is broken at the very end, leave
 # with pytest's own status without running those destructors.  A healthy run never takes this path.
