@@ -42,6 +42,23 @@ class HostDinoViT(HostViT):
         npatch, N = x.shape[1] - 1, self.pos_embed.shape[1] - 1
         if npatch == N and w == h:
             return self.pos_embed
+        # a frozen table resized to the same grid gives the same result every forward (the reference recomputes the
+        # bicubic resize each time, dinov2_vits.py:176-208: 1.7 ms per crop size at ViT-L): cached per (table, grid, dtype)
+        if not self.pos_embed.requires_grad:
+            key = (self.pos_embed.data_ptr(), self.pos_embed._version, str(self.pos_embed.device), w, h, x.dtype)
+            hit = getattr(self, "_pos_cache", {}).get(key)
+            if hit is None:
+                hit = self._interpolate_pos_encoding(x, w, h).detach()
+                cache = getattr(self, "_pos_cache", {})
+                if len(cache) > 8:
+                    cache.clear()
+                cache[key] = hit
+                self._pos_cache = cache
+            return hit
+        return self._interpolate_pos_encoding(x, w, h)
+
+    def _interpolate_pos_encoding(self, x, w, h):
+        npatch, N = x.shape[1] - 1, self.pos_embed.shape[1] - 1
         table = self.pos_embed.float()
         D = x.shape[-1]
         w0, h0 = w // self.patch_size, h // self.patch_size
@@ -122,7 +139,10 @@ def build_dino_backbone(arch, *, img_size: int, patch_size: int, apla_config, at
                 new.proj_weight1.data, new.proj_weight2.data = w[new.trainable_inds], w[new.freezed_inds]
                 new.proj_bias1.data, new.proj_bias2.data = b[new.trainable_inds], b[new.freezed_inds]
             blk.attn = new
-    return fuse_apla_blocks(vit) if fuse else vit
+    if fuse:
+        from .apla.patch_embed import fuse_patch_embed
+        fuse_patch_embed(fuse_apla_blocks(vit))       # frozen stem: patch extraction + tcgen05 GEMM instead of cuDNN
+    return vit
 
 
 class SSLMetaArch(nn.Module):

@@ -104,6 +104,73 @@ def test_fused_block_packed_crops(name, l, n_global, n_local):
     assert rel(blk.attn.proj_bias1.grad, b1.grad) <= 1e-2
 
 
+def test_packed_crop_list_is_passed_on_without_repacking():
+    """Two fused blocks in a row: the PackedCropList the first one returns goes into the second as ONE packed tensor (no
+    torch.cat), and gives the same outputs and the same gradients as a plain list of the same crops (bitwise: same
+    kernels, same inputs)."""
+    _need_gpu()
+    from apla_b200.apla import fuse_apla_blocks
+    from apla_b200.apla.apla_block import PackedCropList
+    model, _, _ = build_case("tiny_r16")
+    D = model.backbone.embed_dim
+    fuse_apla_blocks(model.cuda())
+    b0, b1 = model.backbone.blocks[0], model.backbone.blocks[1]
+    g = torch.Generator().manual_seed(6)
+    crops = [torch.randn(2, 257, D, generator=g), torch.randn(3, 50, D, generator=g)]
+    dys = [torch.randn(c.shape, generator=g).cuda() for c in crops]
+
+    def run(repack):
+        for p in model.parameters():
+            p.grad = None
+        xs = [c.cuda().requires_grad_(True) for c in crops]
+        mid = b0(xs)
+        assert isinstance(mid, PackedCropList) and mid.packed_if_untouched() is not None
+        if repack:
+            mid = [m for m in mid]                   # a plain list: the second block concatenates the views again
+        outs = b1(mid)
+        torch.autograd.backward(list(outs), dys)
+        torch.cuda.synchronize()
+        return [o.detach().clone() for o in outs], [x.grad.clone() for x in xs], b0.attn.proj_weight1.grad.clone()
+
+    o1, g1, w1 = run(False)
+    o2, g2, w2 = run(True)
+    for a, b in zip(o1 + g1, o2 + g2):
+        assert torch.equal(a, b)
+    assert rel(w1, w2) < 1e-6                        # (split-K weight gradient: fp32 atomics)
+    mid = b0([c.cuda() for c in crops])
+    mid[0] = mid[0] * 1.0                            # a modified list must not use the stale packed tensor
+    assert mid.packed_if_untouched() is None
+
+
+@pytest.mark.parametrize("S,patch,D", [(224, 14, 768), (98, 14, 1024), (224, 16, 384)])
+def test_fused_patch_embed_matches_conv(S, patch, D):
+    """FusedPatchEmbed (apla_patchify + tcgen05 GEMM, bf16 operands) against the fp32 convolution it replaces."""
+    _need_gpu()
+    from apla_b200.apla import fuse_patch_embed
+    from apla_b200.hostvit import PatchProjection
+
+    class Holder(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.patch_embed = PatchProjection(S, patch, D)
+
+    torch.manual_seed(3)
+    m = Holder()
+    for p in m.parameters():
+        p.requires_grad = False
+    x = torch.randn(5, 3, S, S)
+    ref = m.patch_embed(x)
+    keys = list(m.state_dict().keys())
+    fuse_patch_embed(m.cuda())
+    assert list(m.state_dict().keys()) == keys
+    out = m.patch_embed(x.cuda())
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    assert rel(out, ref) <= 6e-3
+    m.patch_embed.proj.weight.requires_grad = True
+    with pytest.raises(RuntimeError):
+        m.patch_embed(x.cuda())
+
+
 @pytest.mark.parametrize("name", ["tiny_r16", "c1_vits16_r32_pert", "c2_vitb14_r8"])
 def test_model_of_fused_blocks_matches_reference_golden(name):
     """The host model with fused blocks, driven by plain PyTorch autograd (no step engine): logits, loss and the
