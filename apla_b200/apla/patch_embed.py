@@ -70,3 +70,37 @@ def fuse_patch_embed(model: nn.Module) -> nn.Module:
     if not isinstance(bb.patch_embed, FusedPatchEmbed):
         bb.patch_embed = FusedPatchEmbed(bb.patch_embed)
     return model
+
+
+def cache_pos_encoding(model: nn.Module) -> nn.Module:
+    """Memoise the backbone's position-table resize (`interpolate_pos_encoding`, src/utils/transformers/vit.py:421-437 and
+    dinov2_vits.py:176-208; `pos_for` of the host stand-in): the reference recomputes the bicubic interpolation of a
+    FROZEN table every forward (1-2 ms per call at ViT-B/L).  The result depends on the arguments only
+    through their shapes / dtypes and on the table, so it is cached per (table storage, version, argument signature);
+    a table that requires gradients is never cached."""
+    bb = model if hasattr(model, "pos_embed") else getattr(model, "backbone", None)
+    if bb is None or not hasattr(bb, "pos_embed"):
+        raise AttributeError("model exposes no .pos_embed")
+    for name in ("interpolate_pos_encoding", "pos_for"):
+        fn = getattr(bb, name, None)
+        if fn is None or getattr(fn, "_apla_cached", False):
+            continue
+        cache = {}
+
+        def cached(*args, _fn=fn, _cache=cache, _bb=bb):
+            table = _bb.pos_embed
+            if table.requires_grad and torch.is_grad_enabled():
+                return _fn(*args)
+            sig = tuple((tuple(a.shape), a.dtype, str(a.device)) if torch.is_tensor(a) else a for a in args)
+            key = (table.data_ptr(), table._version, sig)
+            hit = _cache.get(key)
+            if hit is None:
+                if len(_cache) > 8:
+                    _cache.clear()
+                with torch.no_grad():
+                    hit = _cache[key] = _fn(*args).detach()
+            return hit
+
+        cached._apla_cached = True
+        setattr(bb, name, cached)
+    return model

@@ -126,3 +126,24 @@ def test_fuse_apla_blocks_host_logic():
         fuse_apla_blocks(torch.nn.Linear(2, 2))
     # the ctypes mirror of apla_block_weights is the size the library was compiled with
     assert LIB.load().apla_block_weights_size() == ctypes.sizeof(BlockWeights)
+
+
+def test_cache_pos_encoding_is_transparent():
+    """cache_pos_encoding: same values as the un-cached resize, computed once per grid, recomputed when the table changes,
+    and never cached while the table requires gradients."""
+    import torch
+    from apla_b200.apla import cache_pos_encoding
+    from apla_b200.hostvit import HostViT, VitArch
+    torch.manual_seed(0)
+    vit = HostViT(VitArch(128, 2, 2), img_size=56, patch_size=14)
+    vit.pos_embed.requires_grad = False
+    want = vit.pos_for(4).clone()
+    cache_pos_encoding(vit)
+    a, b = vit.pos_for(4), vit.pos_for(4)
+    assert a is b and torch.equal(a, want)
+    assert vit.pos_for(16) is vit.pos_embed or torch.equal(vit.pos_for(16), vit.pos_embed)      # native grid: the table itself
+    with torch.no_grad():
+        vit.pos_embed.mul_(2.0)                                   # in-place update bumps the version: cache miss
+    assert torch.allclose(vit.pos_for(4), 2 * want, atol=1e-6)
+    vit.pos_embed.requires_grad = True
+    assert vit.pos_for(4).requires_grad                           # trainable table: the live computation, with autograd

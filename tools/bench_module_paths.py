@@ -7,6 +7,8 @@ by plain PyTorch autograd / torch.optim -- i.e. what a user gets who keeps the r
                (N x N probabilities in HBM, ~10 ATen kernels around every GEMM) on the same GPU
   attn_only    build_apla(...): only the attention module replaced by the fused APLA_Attention, block glue in eager fp32/bf16
   fused_block  + fuse_apla_blocks(model): every block one autograd node
+  fused_all    + fuse_patch_embed(model) + cache_pos_encoding(model): frozen stem on the library's kernels, position table
+               resized once
   (the step engine = bench.py)
 
 Not a bench.py substitute: informational numbers for DESIGN.md.  Prints one JSON line per path."""
@@ -115,7 +117,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--paths", default="eager_full,attn_only,fused_block,fused_block_r768")
+    ap.add_argument("--paths", default="eager_full,attn_only,fused_block,fused_all,fused_block_r768,fused_all_r768")
     a = ap.parse_args()
     kw = dict(img_size=518, patch_size=14, n_classes=555, seed=0)
     for p in a.paths.split(","):
@@ -131,6 +133,11 @@ def main():
         elif p in ("fused_block", "fused_block_r768"):
             m = build_classifier("vit_base", apla_config=AplaConfig(768 if p.endswith("768") else 8), **kw)
             run(p, fuse_apla_blocks(m), a.batch, a.steps, a.warmup, autocast=False)
+        elif p in ("fused_all", "fused_all_r768"):
+            # + the frozen stem as patchify + tcgen05 GEMM and the position-table resize computed once (round 2)
+            from apla_b200.apla import cache_pos_encoding, fuse_patch_embed
+            m = build_classifier("vit_base", apla_config=AplaConfig(768 if p.endswith("768") else 8), **kw)
+            run(p, cache_pos_encoding(fuse_patch_embed(fuse_apla_blocks(m))), a.batch, a.steps, a.warmup, autocast=False)
         del m
         torch.cuda.empty_cache()
 
