@@ -355,8 +355,9 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __g
       mbar_wait(&ld_full[s], (t >> 1) & 1);
       mbar_wait(sp_full, t & 1);
       tc_fence_after();
-      const float* L = sL + s * 64;
-      const float* Dl = sD + s * 64;
+      // (explicit ld.shared: through the generic pointers these 32 statistic loads per chunk and thread went to the
+      //  local/global queue instead of the shared-memory pipe -- see ptx.cuh)
+      const uint32_t L = smem_u32(sL) + s * 256, Dl = smem_u32(sD) + s * 256;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         if (c * 32 < n_mma) {
@@ -366,16 +367,21 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __g
           tmem_ld_wait();
           uint32_t pp[16], pd[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = c * 32 + 2 * j;
-            const float2 l2 = *reinterpret_cast<const float2*>(L + col);
-            const float2 d2 = *reinterpret_cast<const float2*>(Dl + col);
-            const float p0 = col < valid ? exp2f(__uint_as_float(sv[2 * j]) * sl2 - l2.x) : 0.f;
-            const float p1 = col + 1 < valid ? exp2f(__uint_as_float(sv[2 * j + 1]) * sl2 - l2.y) : 0.f;
-            const float e0 = col < valid ? p0 * (__uint_as_float(dv[2 * j]) - d2.x) : 0.f;
-            const float e1 = col + 1 < valid ? p1 * (__uint_as_float(dv[2 * j + 1]) - d2.y) : 0.f;
-            pp[j] = pack_bf16(p0, p1);
-            pd[j] = pack_bf16(e0, e1);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 l4 = lds_f4(L + (c * 32 + 4 * j4) * 4);
+            const float4 d4 = lds_f4(Dl + (c * 32 + 4 * j4) * 4);
+            const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dl4[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const int j = 2 * j4 + h2;
+              const int col = c * 32 + 2 * j;
+              const float p0 = col < valid ? exp2f(__uint_as_float(sv[2 * j]) * sl2 - lv[2 * h2]) : 0.f;
+              const float p1 = col + 1 < valid ? exp2f(__uint_as_float(sv[2 * j + 1]) * sl2 - lv[2 * h2 + 1]) : 0.f;
+              const float e0 = col < valid ? p0 * (__uint_as_float(dv[2 * j]) - dl4[2 * h2]) : 0.f;
+              const float e1 = col + 1 < valid ? p1 * (__uint_as_float(dv[2 * j + 1]) - dl4[2 * h2 + 1]) : 0.f;
+              pp[j] = pack_bf16(p0, p1);
+              pd[j] = pack_bf16(e0, e1);
+            }
           }
           tmem_st_32x16(lane_addr + c * 16, pp);
           tmem_st_32x16(lane_addr + KV_COL_DP + c * 16, pd);
