@@ -43,6 +43,33 @@ struct Engine {
   std::vector<BlockPtrs> blk;
   std::map<std::string, void*> g;  // global buffers by name
   std::string err;
+  // The APLA weight / bias gradient of a block (a small GEMM + a column sum) depends only on that block's LayerNorm-2
+  // backward and feeds nothing before the optimiser, so it runs on a side stream beside the projection dgrad, the
+  // attention backward and the qkv dgrad -- persistent kernels whose last round leaves most SMs idle (768 (image, head)
+  // groups over 148 CTAs = 5.19 rounds).  Fork / join are events, so the pattern is capturable in the step's CUDA graph.
+  // side_wgrad = number of dsub slots the host allocated (2 enables the side stream for partial_size < dim; the
+  // full-rows path reads dxb and needs none).
+  int side_wgrad = 0;
+  cudaStream_t side = nullptr;
+  std::vector<cudaEvent_t> ev_fork, ev_done;
+  ~Engine() {
+    for (cudaEvent_t ev : ev_fork) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : ev_done) cudaEventDestroy(ev);
+    if (side) cudaStreamDestroy(side);
+  }
+  int side_ready() {
+    if (side) return 0;
+    int lo = 0, hi = 0;
+    APLA_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    APLA_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, lo));   // lowest: the main chain's CTAs go first
+    ev_fork.resize(L);
+    ev_done.resize(L);
+    for (int l = 0; l < L; ++l) {
+      APLA_CUDA(cudaEventCreateWithFlags(&ev_fork[l], cudaEventDisableTiming));
+      APLA_CUDA(cudaEventCreateWithFlags(&ev_done[l], cudaEventDisableTiming));
+    }
+    return 0;
+  }
   int T() const { return B * N; }
   template <class Tp>
   Tp* get(const char* name) {
@@ -168,7 +195,12 @@ static int engine_backward(Engine* e, int l_from, int l_to, cudaStream_t s) {
   void* dH = e->get<void>("gelu_out");     // reused: gradient w.r.t. the fc1 pre-activation
   float* dx = e->get<float>("dx");
   void* dxb = e->get<void>("dxb");
-  void* dsub = e->full_rows ? nullptr : e->get<void>("dsub");
+  char* dsub0 = e->full_rows ? nullptr : e->get<char>("dsub");
+  const size_t dsub_bytes = size_t(T) * e->r_pad * 2;
+  const bool side = e->side_wgrad >= 2 || (e->side_wgrad >= 1 && e->full_rows);
+  if (side) {
+    if (int rc = e->side_ready()) return rc;
+  }
   const int* idx = e->get<int>("idx");
   const int* rowmap = e->full_rows ? e->get<int>("rowmap") : nullptr;
   const Arena ar = arena_of(e);
@@ -205,7 +237,11 @@ static int engine_backward(Engine* e, int l_from, int l_to, cudaStream_t s) {
       return rc;
     if (int rc = gemm_tn(EPI_BIAS, dH, b.wfc1T, R, D, Hd, sH, Hd, dln, nullptr, nullptr, nullptr, nullptr, sD, s, 0))
       return rc;
-    if (cls && dsub) APLA_CUDA(cudaMemsetAsync(dsub, 0, size_t(T) * e->r_pad * 2, s));
+    // dsub alternates between two slots when the weight gradient runs beside the main chain: block l's LayerNorm-2
+    // backward may only overwrite the slot after block l+2's weight gradient has read it
+    void* dsub = dsub0 ? dsub0 + ((side && (l & 1)) ? dsub_bytes : 0) : nullptr;
+    if (side && dsub && l + 2 <= l_from) APLA_CUDA(cudaStreamWaitEvent(s, e->ev_done[l + 2], 0));
+    if (cls && dsub) APLA_CUDA(cudaMemsetAsync(dsub, 0, dsub_bytes, s));
     // dx_mid = dx_out + LN2'(dln); dxb = bf16(gamma1 * dx_mid); dsub = its APLA columns
     if (int rc = layernorm_bwd(dln, sD, x_mid, sD, b.ln2w, dx, sD, dx, sD, dxb, sD, b.g1, dsub,
                                cls ? int64_t(N) * e->r_pad : e->r_pad, idx + size_t(l) * r, r, e->r_pad, R, D, e->eps, s))
@@ -213,13 +249,20 @@ static int engine_backward(Engine* e, int l_from, int l_to, cudaStream_t s) {
     // APLA weight gradient: only the trainable rows of the projection (appla_attn.py:64,70-74)
     float* dW1 = grads + ar.w1 + size_t(l) * r * D;
     float* db1 = grads + ar.b1 + size_t(l) * r;
-    if (e->full_rows) {
-      if (int rc = gemm_wgrad_nt(b.ao, dxb, D, D, T, D, D, dW1, D, rowmap + size_t(l) * D, D, s)) return rc;
-      if (int rc = colsum(dxb, D, T, D, db1, rowmap + size_t(l) * D, s)) return rc;
-    } else {
-      if (int rc = gemm_wgrad_nt(b.ao, dsub, D, e->r_pad, T, D, e->r_pad, dW1, D, nullptr, r, s)) return rc;
-      if (int rc = colsum(dsub, e->r_pad, T, r, db1, nullptr, s)) return rc;
+    cudaStream_t ws = s;
+    if (side) {
+      ws = e->side;
+      APLA_CUDA(cudaEventRecord(e->ev_fork[l], s));
+      APLA_CUDA(cudaStreamWaitEvent(ws, e->ev_fork[l], 0));
     }
+    if (e->full_rows) {
+      if (int rc = gemm_wgrad_nt(b.ao, dxb, D, D, T, D, D, dW1, D, rowmap + size_t(l) * D, D, ws)) return rc;
+      if (int rc = colsum(dxb, D, T, D, db1, rowmap + size_t(l) * D, ws)) return rc;
+    } else {
+      if (int rc = gemm_wgrad_nt(b.ao, dsub, D, e->r_pad, T, D, e->r_pad, dW1, D, nullptr, r, ws)) return rc;
+      if (int rc = colsum(dsub, e->r_pad, T, r, db1, nullptr, ws)) return rc;
+    }
+    if (side) APLA_CUDA(cudaEventRecord(e->ev_done[l], ws));
     if (l == 0) break;  // nothing trainable upstream of block 0's attention
     void* dO = e->get<void>("dO");
     if (cls && e->cls_last >= 2) {
@@ -238,11 +281,14 @@ static int engine_backward(Engine* e, int l_from, int l_to, cudaStream_t s) {
     if (int rc = gemm_tn(EPI_BIAS, e->get<void>("dqkv"), b.wqkvT, T, D, 3 * D, 3 * D, 3 * D, dln, nullptr, nullptr, nullptr,
                          nullptr, D, s, 0))
       return rc;
+    if (side && e->full_rows) APLA_CUDA(cudaStreamWaitEvent(s, e->ev_done[l], 0));   // its weight gradient reads dxb
     // dx_in = dx_mid + LN1'(dln); dxb = bf16(gamma2[l-1] * dx_in) feeds block l-1's MLP branch
     if (int rc = layernorm_bwd(dln, D, x_in, D, b.ln1w, dx, D, dx, D, dxb, D, e->blk[l - 1].g2, nullptr, 0, nullptr, 0, 0,
                                T, D, e->eps, s))
       return rc;
   }
+  // join: the side stream is serial, so the last block's event covers every weight gradient of this range
+  if (side) APLA_CUDA(cudaStreamWaitEvent(s, e->ev_done[l_to], 0));
   return 0;
 }
 
@@ -335,6 +381,10 @@ int apla_engine_set_option(apla_engine_t h, const char* name, int value) {
   APLA_CHECK(e != nullptr && name != nullptr, "apla_engine_set_option: null handle or name");
   if (std::string(name) == "cls_only_last_block") {
     e->cls_last = value < 0 ? 0 : (value > 2 ? 2 : value);
+    return 0;
+  }
+  if (std::string(name) == "side_wgrad") {   // 0 = off, 1 = on for partial_size == dim, 2 = on, "dsub" holds two slots
+    e->side_wgrad = value < 0 ? 0 : (value > 2 ? 2 : value);
     return 0;
   }
   set_error("apla_engine_set_option: unknown option '%s'", name);

@@ -213,6 +213,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       // thread as soon as the LAST sub-load has landed in registers -- not after the math and stores of the tile.
       uint32_t v[2][32];
       [[maybe_unused]] float4 bb[8];   // bias of the NEXT sub-load, fetched right after the current one is consumed
+      if constexpr (EPI == EPI_BIAS_GELU_D) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bb[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // stays zero when there is no bias
+      }
       if (nvalid > 0) {
         tmem_ld_32x32(t_base, v[0]);
         if constexpr (kBias) {
@@ -269,12 +273,22 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[idx & 1][i]);
           const int col = col0 + s * 32;
+          [[maybe_unused]] float bv[32];   // EPI_BIAS_GELU_D adds the bias inside its packed-fp32 math
           if constexpr (kBias) {
-            if (bias) {
+            if constexpr (EPI == EPI_BIAS_GELU_D) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float4 t4 = bb[i];
-                x[4 * i] += t4.x; x[4 * i + 1] += t4.y; x[4 * i + 2] += t4.z; x[4 * i + 3] += t4.w;
+                bv[4 * i] = t4.x; bv[4 * i + 1] = t4.y; bv[4 * i + 2] = t4.z; bv[4 * i + 3] = t4.w;
+              }
+            }
+            if (bias) {
+              if constexpr (EPI != EPI_BIAS_GELU_D) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 t4 = bb[i];
+                  x[4 * i] += t4.x; x[4 * i + 1] += t4.y; x[4 * i + 2] += t4.z; x[4 * i + 3] += t4.w;
+                }
               }
               if (idx + 1 < NSUB && idx + 1 < nvalid) {
                 const int j1 = (idx + 1) / SUBS, s1 = (idx + 1) % SUBS;
@@ -309,13 +323,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             for (int c = 0; c < 4; ++c) {
               uint32_t dd[4], g[4];
 #pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                float g0, g1, d0, d1;
-                gelu_erf_both(x[8 * c + 2 * t], g0, d0);
-                gelu_erf_both(x[8 * c + 2 * t + 1], g1, d1);
-                g[t] = pack_bf16(g0, g1);
-                dd[t] = pack_f16(d0, d1);
-              }
+              for (int t = 0; t < 4; ++t)
+                gelu_erf_both_x2(x[8 * c + 2 * t], x[8 * c + 2 * t + 1], bv[8 * c + 2 * t], bv[8 * c + 2 * t + 1], g[t], dd[t]);
               const uint32_t off = lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4);   // 64B-swizzled row of 32 x 2 bytes
               sts128(buf + off, dd[0], dd[1], dd[2], dd[3]);
               sts128(buf + kStgBuf / 2 + off, g[0], g[1], g[2], g[3]);

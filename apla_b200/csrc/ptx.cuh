@@ -383,4 +383,54 @@ __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
 }
 __device__ __forceinline__ float2 unpack_f16(uint32_t v) { return __half22float2(*reinterpret_cast<__half2*>(&v)); }
 
+// Packed fp32 pairs (FFMA2 / FMUL2 / FADD2 of sm_100): one issue slot for two lanes' worth of IEEE fp32 math -- the
+// results are bit-identical to the scalar instructions, only the instruction count of an issue-bound epilogue halves.
+struct f32x2 { uint64_t v; };
+__device__ __forceinline__ f32x2 f2_make(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_split(f32x2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_bcast(float c) { return f2_make(c, c); }
+
+// gelu_erf_both for two neighbouring elements (+ their bias) in packed fp32; g as bf16x2, gelu' as fp16x2
+__device__ __forceinline__ void gelu_erf_both_x2(float x0, float x1, float b0, float b1, uint32_t& g_bf16x2, uint32_t& d_f16x2) {
+  const f32x2 x = f2_add(f2_make(x0, x1), f2_make(b0, b1));
+  float q0, q1;
+  f2_split(f2_mul(x, x), q0, q1);
+  const f32x2 x2 = f2_make(fminf(q0, 49.0f), fminf(q1, 49.0f));
+  f32x2 p = f2_fma(x2, f2_bcast(kGeluC2 * kNegLog2e), f2_bcast(kGeluC1 * kNegLog2e));
+  p = f2_fma(x2, p, f2_bcast(kGeluC0 * kNegLog2e));
+  f32x2 u1 = f2_fma(x2, f2_bcast(5.0f * kGeluC2), f2_bcast(3.0f * kGeluC1));
+  u1 = f2_fma(x2, u1, f2_bcast(kGeluC0));
+  float a0, a1;
+  f2_split(f2_mul(x, p), a0, a1);
+  float e0, e1;
+  f2_split(f2_add(f2_make(ex2_approx(a0), ex2_approx(a1)), f2_bcast(1.0f)), e0, e1);
+  const f32x2 s = f2_make(rcp_approx(e0), rcp_approx(e1));
+  float g0, g1, d0, d1;
+  f2_split(f2_mul(x, s), g0, g1);
+  const f32x2 w = f2_mul(f2_mul(x, u1), s);
+  const f32x2 t = f2_fma(s, f2_bcast(-1.0f), f2_bcast(1.0f));
+  f2_split(f2_fma(w, t, s), d0, d1);
+  g_bf16x2 = pack_bf16(g0, g1);
+  d_f16x2 = pack_f16(d0, d1);
+}
+
 }  // namespace apla

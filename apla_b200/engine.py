@@ -119,6 +119,9 @@ class FineTuneEngine:
         if not self._handle:
             raise RuntimeError("apla_engine_create failed: " + LIB.last_error())
         LIB.call("apla_engine_set_option", self._handle, b"cls_only_last_block", int(self.cls_only_last_block))
+        # measured: no gain on C2 (7.94 vs 7.98 ms), +0.4 % on C3 -- the step runs into the power cap, not into idle SMs;
+        # kept as an option (APLA_SIDE_WGRAD=1), off by default
+        self.side_wgrad = os.environ.get("APLA_SIDE_WGRAD", "0") != "0"
 
         # ---- embedding ----
         wpe = torch.zeros(D, kpad, dtype=F32)
@@ -249,7 +252,10 @@ class FineTuneEngine:
         if full_rows:
             self._set("rowmap", self._dev(rowmap_all, torch.int32))
         else:
-            self._set("dsub", self._new(T, r_pad))
+            self._set("dsub", self._new(2 if self.side_wgrad else 1, T, r_pad))
+        # weight / bias gradients of a block on the engine's side stream beside the projection dgrad, the attention
+        # backward and the qkv dgrad (csrc/engine.cu, Engine::side_wgrad) when APLA_SIDE_WGRAD=1
+        LIB.call("apla_engine_set_option", self._handle, b"side_wgrad", (1 if full_rows else 2) if self.side_wgrad else 0)
         self._hyper_dev = self._new(3, dtype=F32, zero=True)
         if self.use_graph:
             self._set("hyper", self._hyper_dev)
@@ -482,7 +488,11 @@ class FineTuneEngine:
 
             def capture(fn):
                 gr = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gr, capture_error_mode="thread_local"):
+                # captured on a high-priority stream: the kernel nodes inherit it, so the main chain's CTAs are placed
+                # before those of the lowest-priority side branch (weight gradients) whenever both are pending
+                if getattr(self, "_cap_stream", None) is None:
+                    self._cap_stream = torch.cuda.Stream(device=self.device, priority=-1)
+                with torch.cuda.graph(gr, stream=self._cap_stream, capture_error_mode="thread_local"):
                     fn()
                 return gr
 
