@@ -36,6 +36,13 @@ int apla_gemm_bias_ls_residual_fwd(const void* A, int lda, const void* W, int ld
                                    apla_stream_t stream) {
   return gemm_tn(EPI_RESID, A, W, M, N, K, lda, ldw, out, nullptr, bias, gamma, resid, ldo, S(stream), 0);
 }
+int apla_gemm_bias_ls_residual_ln_fwd(const void* A, int lda, const void* W, int ldw, const float* bias,
+                                      const float* gamma, const float* resid, float* out, int ldo, const float* ln_w,
+                                      const float* ln_b, void* ln_out, int ld_ln, float eps, int M, int N, int K,
+                                      int one_launch, apla_stream_t stream) {
+  return gemm_resid_ln(A, W, M, N, K, lda, ldw, out, bias, gamma, resid, ldo, ln_w, ln_b, ln_out, ld_ln, eps, S(stream),
+                       one_launch);
+}
 int apla_gemm_bias_ls_accumulate(const void* A, int lda, const void* W, int ldw, const float* bias, const float* gamma,
                                  float* out, int ldo, int M, int N, int K, apla_stream_t stream) {
   return gemm_tn(EPI_RED, A, W, M, N, K, lda, ldw, out, nullptr, bias, gamma, nullptr, ldo, S(stream), 0);

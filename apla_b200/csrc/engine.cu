@@ -150,7 +150,10 @@ static int engine_forward(Engine* e, const float* images, const int64_t* labels,
     float* x_in = xs + size_t(2 * l) * TD;
     float* x_mid = xs + size_t(2 * l + 1) * TD;
     float* x_out = xs + size_t(2 * l + 2) * TD;
-    if (int rc = layernorm_fwd(x_in, D, b.ln1w, b.ln1b, ln_out, D, T, D, e->eps, s)) return rc;
+    // LayerNorm 1: block 0 normalises the embedded tokens; later blocks get it from the previous block's fc2 launch
+    if (l == 0) {
+      if (int rc = layernorm_fwd(x_in, D, b.ln1w, b.ln1b, ln_out, D, T, D, e->eps, s)) return rc;
+    }
     if (int rc = gemm_tn(EPI_BIAS, ln_out, b.wqkv, T, 3 * D, D, D, D, b.qkv, nullptr, b.bqkv, nullptr, nullptr, 3 * D, s, 0))
       return rc;
     // rows / row strides of the per-token tail of the block: every token, or the CLS rows of the last block
@@ -162,12 +165,22 @@ static int engine_forward(Engine* e, const float* images, const int64_t* labels,
     }
     const int R = cls ? B : T;
     const int sD = cls ? N * D : D, sH = cls ? N * Hd : Hd;
-    if (int rc = gemm_tn(EPI_RESID, b.ao, b.wproj, R, D, D, sD, D, x_mid, nullptr, b.bproj, b.g1, x_in, sD, s, 0)) return rc;
-    if (int rc = layernorm_fwd(x_mid, sD, b.ln2w, b.ln2b, ln_out, sD, R, D, e->eps, s)) return rc;
+    // projection (+bias, LayerScale, residual) and LayerNorm 2 in one launch
+    if (int rc = gemm_resid_ln(b.ao, b.wproj, R, D, D, sD, D, x_mid, b.bproj, b.g1, x_in, sD, b.ln2w, b.ln2b, ln_out, sD,
+                               e->eps, s))
+      return rc;
     if (int rc = gemm_tn(EPI_BIAS_GELU_D, ln_out, b.wfc1, R, Hd, D, sD, D, b.hpre, gelu_out, b.bfc1, nullptr, nullptr, sH, s, 0))
       return rc;
-    if (int rc = gemm_tn(EPI_RESID, gelu_out, b.wfc2, R, D, Hd, sH, Hd, x_out, nullptr, b.bfc2, b.g2, x_mid, sD, s, 0))
-      return rc;
+    if (l + 1 < L) {
+      // fc2 (+bias, LayerScale, residual) and the NEXT block's LayerNorm 1 in one launch
+      const BlockPtrs& nb = e->blk[l + 1];
+      if (int rc = gemm_resid_ln(gelu_out, b.wfc2, R, D, Hd, sH, Hd, x_out, b.bfc2, b.g2, x_mid, sD, nb.ln1w, nb.ln1b, ln_out,
+                                 sD, e->eps, s))
+        return rc;
+    } else {
+      if (int rc = gemm_tn(EPI_RESID, gelu_out, b.wfc2, R, D, Hd, sH, Hd, x_out, nullptr, b.bfc2, b.g2, x_mid, sD, s, 0))
+        return rc;
+    }
   }
 
   // ---- final norm on the CLS rows only (vit.py:417-419), head, loss ----

@@ -398,6 +398,22 @@ int gemm_tn(int epi, const void* A, const void* B, int M, int N, int K, int lda,
   return 1;
 }
 
+int gemm_resid_ln(const void* A, const void* B, int M, int N, int K, int lda, int ldb, float* out, const float* bias,
+                  const float* gamma, const float* resid, int ldo, const float* ln_w, const float* ln_b, void* ln_out,
+                  int ld_ln, float eps, cudaStream_t stream, int fuse_mode) {
+  // fuse_mode: 1 = one launch, 0 = two launches, < 0 = default, which is one launch only with APLA_GEMM_LN_FUSE=1.  Measured on the C2 step (B200, 50 steps): 8.69 ms fused against 7.93 ms with
+  // the two launches -- results bit-identical, but the LayerNorm of a slab lands on the epilogue warps of whichever CTA
+  // finishes the slab's last column tile, and those warps are what the K = 768 residual GEMM is already bound by (tensor
+  // pipe 36 % busy); the stand-alone row kernel at full occupancy streams the same bytes at 6.3 TB/s.  Kept as an option.
+  static const bool fuse = [] { const char* e = getenv("APLA_GEMM_LN_FUSE"); return e && atoi(e) != 0; }();
+  static const int impl = [] { const char* e = getenv("APLA_GEMM_IMPL"); return e ? atoi(e) : 2; }();
+  const bool want = fuse_mode < 0 ? fuse : fuse_mode != 0;
+  if (want && impl == 2 && gemm2_resid_ln_supported(N) && K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldo % 8 == 0)
+    return gemm2_resid_ln(A, B, M, N, K, lda, ldb, out, bias, gamma, resid, ldo, ln_w, ln_b, ln_out, ld_ln, eps, stream);
+  if (int rc = gemm_tn(EPI_RESID, A, B, M, N, K, lda, ldb, out, nullptr, bias, gamma, resid, ldo, stream, 0)) return rc;
+  return layernorm_fwd(out, ldo, ln_w, ln_b, ln_out, ld_ln, M, N, eps, stream);
+}
+
 // Weight gradient  dW[rowmap(n), m] += sum_k A[k, m] * B[k, n]   (A = layer input X [K=T, M=D_in],
 // B = output gradient dY [K=T, N]); fp32 atomics over k_splits partial sums, dW must be zero-initialised.
 int gemm_wgrad_nt(const void* A, const void* B, int M, int N, int K, int lda, int ldb, float* dW, int ldw,

@@ -14,6 +14,10 @@
 // Epilogues: see kernels.cuh / gemm.cu header (EPI_BIAS, EPI_BIAS_GELU, EPI_RESID, EPI_GELU_BWD), plus
 //   EPI_BIAS_GELU_D  h = acc + bias[n] (fp32, not stored);  out_f16 = gelu_erf'(h);  out2_bf16 = gelu_erf(h)
 //   EPI_MUL_F16      out_bf16 = acc * aux_f16[m,n]   (fc2 dgrad times the saved GELU derivative)
+//   EPI_RESID_LN     EPI_RESID, then the LayerNorm that reads the new residual stream: the CTA that completes the LAST
+//                    column tile of a 128-row slab (a self-resetting arrival counter per slab in global memory)
+//                    re-reads the slab -- still in L2 -- and writes bf16((x - mean) * rstd * w + b), the A operand of
+//                    the next GEMM.  Same arithmetic as ln_fwd_kernel (rowwise.cu), minus its launch and its DRAM pass.
 //   EPI_DELTA  out_bf16 = acc;  rowstat[m, n/64] = sum over the 64-wide head of bf16(acc) * aux_bf16[m, n]
 //              (attention-projection dgrad fused with FlashAttention's delta = rowsum(dO * O); one staging chunk is
 //              exactly one head and one thread owns one row of it, so the reduction needs no shuffles).
@@ -60,12 +64,74 @@ __device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {
   return r;
 }
 
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct LnArgs {
+  const float* x;   // the fp32 output of this GEMM (read back by generic loads)
+  int64_t ldx;
+  const float* w;
+  const float* b;
+  __nv_bfloat16* out;
+  int* counters;   // [row slabs of 128] arrival counters, zero between launches (the last arriver resets its slab's)
+  int ld;
+  float eps;
+};
+
+// LayerNorm of `nrows` consecutive rows (two at a time: the loads of both are in flight together) by one warp;
+// D = NV * 128.  ld.global.cg: the rows were just written through L2 by TMA stores of this and other CTAs.
+template <int NV>
+__device__ __forceinline__ void ln_rows(const LnArgs& ln, int row0, int nrows, int M, int lane) {
+  const float* x = ln.x;
+  const int64_t ldx = ln.ldx;
+  constexpr float inv_d = 1.f / float(NV * 128);
+  for (int r = 0; r < nrows; r += 2) {
+    float4 v[2][NV];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int row = row0 + r + t;
+      const float4* xr = reinterpret_cast<const float4*>(x + int64_t(row) * ldx);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[t][i] = (row < M && r + t < nrows) ? __ldcg(xr + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int row = row0 + r + t;
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) s += v[t][i].x + v[t][i].y + v[t][i].z + v[t][i].w;
+      const float mean = warp_sum(s) * inv_d;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        v[t][i].x -= mean; v[t][i].y -= mean; v[t][i].z -= mean; v[t][i].w -= mean;
+        q += v[t][i].x * v[t][i].x + v[t][i].y * v[t][i].y + v[t][i].z * v[t][i].z + v[t][i].w * v[t][i].w;
+      }
+      const float rstd = rsqrtf(warp_sum(q) * inv_d + ln.eps);
+      if (row < M && r + t < nrows) {
+        uint2* yr = reinterpret_cast<uint2*>(ln.out + int64_t(row) * ln.ld);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const float4 ww = __ldg(reinterpret_cast<const float4*>(ln.w) + lane + 32 * i);
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(ln.b) + lane + 32 * i);
+          yr[lane + 32 * i] = make_uint2(pack_bf16(v[t][i].x * rstd * ww.x + bb.x, v[t][i].y * rstd * ww.y + bb.y),
+                                         pack_bf16(v[t][i].z * rstd * ww.z + bb.z, v[t][i].w * rstd * ww.w + bb.w));
+        }
+      }
+    }
+  }
+}
+
 template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
              const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_out2,
              const __grid_constant__ CUtensorMap tma_aux, int M, int N, int K, const float* __restrict__ bias,
-             const float* __restrict__ gamma, float* __restrict__ rowstat) {
+             const float* __restrict__ gamma, float* __restrict__ rowstat, const LnArgs ln) {
   using C = Cfg<BN>;
   constexpr int kStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -77,6 +143,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
   uint64_t* tempty = tfull + 2;
   uint64_t* aux_full = tempty + 2;  // [kEpiWarps][2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 2 * kEpiWarps);
+  [[maybe_unused]] volatile uint32_t* ln_flag = tmem_slot + 1;   // EPI_RESID_LN: "this CTA completed the slab"
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -93,7 +160,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     tma_prefetch_desc(&tma_b);
     tma_prefetch_desc(&tma_out);
     if constexpr (EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_GELU_D) tma_prefetch_desc(&tma_out2);
-    if constexpr (EPI == EPI_RESID || EPI == EPI_GELU_BWD || EPI == EPI_DELTA || EPI == EPI_MUL_F16) tma_prefetch_desc(&tma_aux);
+    if constexpr (EPI == EPI_RESID || EPI == EPI_RESID_LN || EPI == EPI_GELU_BWD || EPI == EPI_DELTA || EPI == EPI_MUL_F16) tma_prefetch_desc(&tma_aux);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -167,8 +234,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue warps (both CTAs) =====================
-    constexpr bool kF32 = (EPI == EPI_RESID || EPI == EPI_RED);
-    constexpr bool kAux = (EPI == EPI_RESID || EPI == EPI_GELU_BWD || EPI == EPI_DELTA || EPI == EPI_MUL_F16);
+    constexpr bool kLN = (EPI == EPI_RESID_LN);
+    constexpr bool kF32 = (EPI == EPI_RESID || kLN || EPI == EPI_RED);
+    constexpr bool kAux = (EPI == EPI_RESID || kLN || EPI == EPI_GELU_BWD || EPI == EPI_DELTA || EPI == EPI_MUL_F16);
     constexpr bool kBias = (EPI != EPI_GELU_BWD && EPI != EPI_DELTA && EPI != EPI_MUL_F16);
     constexpr bool kTwoOut = (EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_GELU_D);
     // columns per chunk: one 128-byte staging row, except the two-output GELU epilogue which packs a 64-byte row of
@@ -186,12 +254,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     uint32_t cnt = 0;  // running chunk counter: staging buffer = cnt & 1 (alternates across tiles too)
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    // EPI_RESID_LN: the arrival for a tile's 128-row slab is made one tile late (or at the end), when its stores have
+    // drained anyway; whoever brings a slab's count to num_n normalises it.
+    [[maybe_unused]] int pend_slab = -1;
+    for (int tile = cluster_id; kLN || tile < num_tiles; tile += num_clusters) {
       const int row0 = (tile / num_n) * (2 * BM) + int(cta_rank) * BM + q * 32;  // this warp's 32-row slab
       const int n0 = (tile % num_n) * BN;
       // 32-column sub-loads of this warp that lie inside the matrix (warp-uniform; N % 32 == 0)
       int nvalid = 0;
-      if (row0 < M) {
+      if (row0 < M && tile < num_tiles) {
 #pragma unroll
         for (int i = 0; i < NSUB; ++i) nvalid += (n0 + (half + 2 * (i / SUBS)) * CW + (i % SUBS) * 32 < N) ? 1 : 0;
       }
@@ -204,6 +275,37 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
           tma_load_2d(reinterpret_cast<void*>(staging + ew * 2 * kStgBuf + b0 * kStgBuf), &tma_aux, &abar[b0],
                       n0 + half * CW, row0);
         }
+      }
+      if constexpr (kLN) {
+        // (one call site, written out: a lambda called from two places was not inlined and put its captures in local memory)
+        if (pend_slab >= 0) {
+          const int slab = pend_slab;
+          if (lane == 0) {
+            tma_store_wait<0>();                                   // this warp's rows of the slab are in global memory
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            __threadfence();
+          }
+          __syncwarp();
+          epi_bar_sync();
+          if (ew == 0 && lane == 0) {
+            const int old = atomicAdd(ln.counters + slab, 1);
+            const bool last = old == num_n - 1;
+            if (last) ln.counters[slab] = 0;                        // ready for the next launch
+            __threadfence();
+            *ln_flag = last ? 1u : 0u;
+          }
+          epi_bar_sync();
+          if (*ln_flag != 0) {   // rewritten only behind the next epi_bar_sync, which every warp reaches after this read
+            const int r0 = slab * BM + ew * (BM / kEpiWarps);
+            switch (N >> 7) {
+              case 3: ln_rows<3>(ln, r0, BM / kEpiWarps, M, lane); break;
+              case 6: ln_rows<6>(ln, r0, BM / kEpiWarps, M, lane); break;
+              default: ln_rows<8>(ln, r0, BM / kEpiWarps, M, lane); break;
+            }
+          }
+        }
+        if (tile >= num_tiles) break;
+        pend_slab = (tile / num_n) * 2 + int(cta_rank);
       }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
@@ -219,7 +321,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       }
       if (nvalid > 0) {
         tmem_ld_32x32(t_base, v[0]);
-        if constexpr (kBias) {
+        if constexpr (kBias && !kLN) {   // (EPI_RESID_LN reads the bias at its use: it needs the 32 registers)
           if (bias) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) bb[i] = __ldg(reinterpret_cast<const float4*>(bias + n0 + half * CW) + i);
@@ -283,14 +385,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
               }
             }
             if (bias) {
-              if constexpr (EPI != EPI_BIAS_GELU_D) {
+              if constexpr (kLN) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 t4 = __ldg(reinterpret_cast<const float4*>(bias + col) + i);
+                  x[4 * i] += t4.x; x[4 * i + 1] += t4.y; x[4 * i + 2] += t4.z; x[4 * i + 3] += t4.w;
+                }
+              } else if constexpr (EPI != EPI_BIAS_GELU_D) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                   const float4 t4 = bb[i];
                   x[4 * i] += t4.x; x[4 * i + 1] += t4.y; x[4 * i + 2] += t4.z; x[4 * i + 3] += t4.w;
                 }
               }
-              if (idx + 1 < NSUB && idx + 1 < nvalid) {
+              if (!kLN && idx + 1 < NSUB && idx + 1 < nvalid) {
                 const int j1 = (idx + 1) / SUBS, s1 = (idx + 1) % SUBS;
                 const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + (half + 2 * j1) * CW + s1 * 32);
 #pragma unroll
@@ -352,7 +460,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
               sts128(stg_addr(buf, lane, c), __float_as_uint(g.x * x[4 * c]), __float_as_uint(g.y * x[4 * c + 1]),
                      __float_as_uint(g.z * x[4 * c + 2]), __float_as_uint(g.w * x[4 * c + 3]));
             }
-          } else if constexpr (EPI == EPI_RESID) {
+          } else if constexpr (EPI == EPI_RESID || EPI == EPI_RESID_LN) {
             const float4* g4 = reinterpret_cast<const float4*>(gamma ? gamma + col : nullptr);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -430,13 +538,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
 
 template <int BN, int EPI>
 static int launch(const void* A, const void* B, int M, int N, int K, int lda, int ldb, void* out, void* out2,
-                  const float* bias, const float* gamma, const void* aux, int ldo, cudaStream_t stream) {
+                  const float* bias, const float* gamma, const void* aux, int ldo, cudaStream_t stream,
+                  const LnArgs& ln = LnArgs{}) {
   float* rowstat = EPI == EPI_DELTA ? reinterpret_cast<float*>(out2) : nullptr;
   using C = Cfg<BN>;
   CUtensorMap ta, tb, to, to2, tx;
   if (int rc = make_tmap_2d(&ta, A, 2, M, K, lda, BM, BK, true)) return rc;
   if (int rc = make_tmap_2d(&tb, B, 2, N, K, ldb, BN / 2, BK, true)) return rc;
-  constexpr int oelt = (EPI == EPI_RESID || EPI == EPI_RED) ? 4 : 2;
+  constexpr int oelt = (EPI == EPI_RESID || EPI == EPI_RESID_LN || EPI == EPI_RED) ? 4 : 2;
   if (EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_GELU_D) {
     if (int rc = make_tmap_2d_sw(&to, out, 2, M, N, ldo, 32, 32, 64)) return rc;
     if (int rc = make_tmap_2d_sw(&to2, out2, 2, M, N, ldo, 32, 32, 64)) return rc;
@@ -445,7 +554,7 @@ static int launch(const void* A, const void* B, int M, int N, int K, int lda, in
     to2 = to;
   }
   tx = to;
-  if (EPI == EPI_RESID || EPI == EPI_GELU_BWD || EPI == EPI_DELTA || EPI == EPI_MUL_F16)
+  if (EPI == EPI_RESID || EPI == EPI_RESID_LN || EPI == EPI_GELU_BWD || EPI == EPI_DELTA || EPI == EPI_MUL_F16)
     if (int rc = make_tmap_2d(&tx, aux, oelt, M, N, ldo, 32, 128 / oelt, true)) return rc;
   auto kern = gemm2_kernel<BN, EPI>;
   static bool attr_set = false;
@@ -456,7 +565,7 @@ static int launch(const void* A, const void* B, int M, int N, int K, int lda, in
   const int tiles = cdiv(M, 2 * BM) * cdiv(N, BN);
   const int max_clusters = sm_count() / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  kern<<<2 * clusters, kThreads, C::kSmemBytes, stream>>>(ta, tb, to, to2, tx, M, N, K, bias, gamma, rowstat);
+  kern<<<2 * clusters, kThreads, C::kSmemBytes, stream>>>(ta, tb, to, to2, tx, M, N, K, bias, gamma, rowstat, ln);
   APLA_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -479,6 +588,29 @@ static int dispatch(const void* A, const void* B, int M, int N, int K, int lda, 
 }
 
 }  // namespace g2
+
+// out_f32 = resid + gamma * (A B^T + bias), ln_out_bf16 = LayerNorm(out_f32; ln_w, ln_b) in the same launch.
+bool gemm2_resid_ln_supported(int N) { return N == 384 || N == 768 || N == 1024; }
+
+int gemm2_resid_ln(const void* A, const void* B, int M, int N, int K, int lda, int ldb, float* out, const float* bias,
+                   const float* gamma, const float* resid, int ldo, const float* ln_w, const float* ln_b, void* ln_out,
+                   int ld_ln, float eps, cudaStream_t stream) {
+  APLA_CHECK(gemm2_resid_ln_supported(N), "gemm2_resid_ln: N=%d is not 384 / 768 / 1024", N);
+  APLA_CHECK(ln_w && ln_b && ln_out && resid && ld_ln % 4 == 0 && ldo % 4 == 0, "gemm2_resid_ln: bad LayerNorm arguments");
+  // arrival counters, one per 128-row slab: zero at allocation, every launch leaves them zero again.  One allocation per
+  // device; launches that use it must be stream-ordered with respect to each other (they are: one step, one stream).
+  constexpr int kMaxSlabs = 1 << 16;
+  static int* counters[64] = {};
+  int dev = 0;
+  APLA_CUDA(cudaGetDevice(&dev));
+  APLA_CHECK(dev < 64 && cdiv(M, g2::BM) <= kMaxSlabs, "gemm2_resid_ln: device %d / M=%d out of range", dev, M);
+  if (!counters[dev]) {
+    APLA_CUDA(cudaMalloc(&counters[dev], kMaxSlabs * sizeof(int)));
+    APLA_CUDA(cudaMemset(counters[dev], 0, kMaxSlabs * sizeof(int)));
+  }
+  g2::LnArgs ln{out, int64_t(ldo), ln_w, ln_b, reinterpret_cast<__nv_bfloat16*>(ln_out), counters[dev], ld_ln, eps};
+  return g2::launch<256, EPI_RESID_LN>(A, B, M, N, K, lda, ldb, out, nullptr, bias, gamma, resid, ldo, stream, ln);
+}
 
 int gemm2_tn(int epi, const void* A, const void* B, int M, int N, int K, int lda, int ldb, void* out, void* out2,
              const float* bias, const float* gamma, const void* aux, int ldo, cudaStream_t stream, int bn) {

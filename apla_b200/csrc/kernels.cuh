@@ -6,7 +6,7 @@
 namespace apla {
 
 enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_RESID = 2, EPI_GELU_BWD = 3, EPI_F32_T = 4, EPI_DELTA = 5, EPI_BIAS_GELU_D = 6,
-       EPI_MUL_F16 = 7, EPI_RED = 8 };
+       EPI_MUL_F16 = 7, EPI_RED = 8, EPI_RESID_LN = 9 };
 
 // gemm.cu
 int gemm_tn(int epi, const void* A, const void* B, int M, int N, int K, int lda, int ldb, void* out, void* out2,
@@ -15,6 +15,15 @@ int gemm2_tn(int epi, const void* A, const void* B, int M, int N, int K, int lda
              const float* bias, const float* gamma, const void* aux, int ldo, cudaStream_t stream, int bn);
 int gemm_wgrad_nt(const void* A, const void* B, int M, int N, int K, int lda, int ldb, float* dW, int ldw,
                   const int* rowmap, int n_valid, cudaStream_t stream);
+// out_f32 = resid + gamma * (A B^T + bias) and ln_out_bf16 = LayerNorm(out_f32): one launch when the 2-CTA kernel covers
+// the width (gemm2.cu, EPI_RESID_LN), otherwise the residual GEMM followed by layernorm_fwd
+int gemm_resid_ln(const void* A, const void* B, int M, int N, int K, int lda, int ldb, float* out, const float* bias,
+                  const float* gamma, const float* resid, int ldo, const float* ln_w, const float* ln_b, void* ln_out,
+                  int ld_ln, float eps, cudaStream_t stream, int fuse_mode = -1);
+bool gemm2_resid_ln_supported(int N);
+int gemm2_resid_ln(const void* A, const void* B, int M, int N, int K, int lda, int ldb, float* out, const float* bias,
+                   const float* gamma, const float* resid, int ldo, const float* ln_w, const float* ln_b, void* ln_out,
+                   int ld_ln, float eps, cudaStream_t stream);
 
 // attention.cu (dispatch), attention_tc.cu / attention_tc_bwd.cu (streaming tcgen05 kernels, any sequence length)
 int attn_fwd(const void* qkv, void* out, float* lse, const int* cu_seqlens, int num_seqs, int max_seqlen,

@@ -65,6 +65,23 @@ def gemm_bias_ls_residual(a, w, bias, gamma, resid, out=None):
     return out
 
 
+def gemm_bias_ls_residual_ln(a, w, bias, gamma, resid, ln_w, ln_b, eps: float, out=None, ln_out=None, one_launch: int = -1):
+    """out_f32 = resid + gamma * (a @ w^T + bias) and ln_out_bf16 = LayerNorm(out_f32); one_launch=1 asks for the single
+    fused launch (widths 384 / 768 / 1024), 0 for the two kernels, -1 for the library default.  -> (out, ln_out)."""
+    require_device()
+    _chk(a, BF16, "a", 2); _chk(w, BF16, "w", 2); _chk(resid, F32, "resid", 2)
+    _chk(ln_w, F32, "ln_w", 1); _chk(ln_b, F32, "ln_b", 1)
+    M, K = a.shape; N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=F32)
+    if ln_out is None:
+        ln_out = torch.empty(M, N, device=a.device, dtype=BF16)
+    assert _ld(out) == _ld(resid)
+    LIB.call("apla_gemm_bias_ls_residual_ln_fwd", ptr(a), _ld(a), ptr(w), _ld(w), ptr(bias), ptr(gamma), ptr(resid),
+             ptr(out), _ld(out), ptr(ln_w), ptr(ln_b), ptr(ln_out), _ld(ln_out), float(eps), M, N, K, int(one_launch), stream())
+    return out, ln_out
+
+
 def gemm_dgrad(dy, wt, out=None):
     """dx[M,Kin] = dy[M,Nout] @ wt[Kin,Nout]^T with wt the pre-transposed frozen weight."""
     require_device()

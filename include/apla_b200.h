@@ -44,6 +44,17 @@ int apla_gemm_bias_gelu_fwd(const void* A, int lda, const void* W, int ldw, cons
 int apla_gemm_bias_ls_residual_fwd(const void* A, int lda, const void* W, int ldw, const float* bias,
                                    const float* gamma, const float* resid, float* out, int ldo, int M, int N, int K,
                                    apla_stream_t stream);
+/* The residual update above FOLLOWED BY the LayerNorm that reads it, in one launch:
+ *   out_f32 = resid_f32 + gamma * (A . W^T + bias);  ln_out_bf16[M,N] = (out - mean) * rstd * ln_w + ln_b
+ * i.e. vit.py:284 + the norm2 of vit.py:285 (projection), or vit.py:285 + the norm1 of the next block's vit.py:280 (fc2).
+ * one_launch = 0: the two kernels back to back.  one_launch = 1 and N = 384 / 768 / 1024: ONE launch -- the CTA that
+ * completes the last column tile of a 128-row slab normalises the slab while it is still in L2 (bit-identical results;
+ * measured slower on the C2 step).  one_launch < 0: the default = two kernels unless
+ * APLA_GEMM_LN_FUSE=1.  One-launch calls on one device must be stream-ordered (shared arrival counters). */
+int apla_gemm_bias_ls_residual_ln_fwd(const void* A, int lda, const void* W, int ldw, const float* bias,
+                                      const float* gamma, const float* resid, float* out, int ldo, const float* ln_w,
+                                      const float* ln_b, void* ln_out, int ld_ln, float eps, int M, int N, int K,
+                                      int one_launch, apla_stream_t stream);
 /* out_f32[M,N] += gamma_f32[N] * (A . W^T + bias): the same residual update performed IN PLACE -- the epilogue hands
  * the scaled tile to the L2 as a TMA reduce-add, so the fp32 residual never passes through shared memory. */
 int apla_gemm_bias_ls_accumulate(const void* A, int lda, const void* W, int ldw, const float* bias, const float* gamma,

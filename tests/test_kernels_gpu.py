@@ -86,6 +86,33 @@ def test_gemm_ls_residual_inplace():
     assert rel(r2, resid + (a.float() @ w.float().t() + bias)) < 1e-3
 
 
+@pytest.mark.parametrize("M,N,K", [(16448, 768, 768), (1028, 768, 3072), (4099, 1024, 1024), (300, 384, 384), (64, 768, 768),
+                                   (2000, 512, 256)])
+def test_gemm_ls_residual_layernorm_one_launch(M, N, K):
+    """The residual GEMM that also normalises its output (the slab's last column tile triggers the LayerNorm) against the
+    two launches it replaces: identical residual stream, LayerNorm output equal to apla_layernorm_fwd of it -- repeated,
+    because the hand-over between CTAs is a race if it is wrong."""
+    ops = _cuda()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = bf(torch.randn(M, K, device="cuda", generator=g))
+    w = bf(torch.randn(N, K, device="cuda", generator=g) * 0.03)
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    gamma = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g) * 2 + 0.3
+    ln_w = torch.randn(N, device="cuda", generator=g)
+    ln_b = torch.randn(N, device="cuda", generator=g) * 0.1
+    x_ref = ops.gemm_bias_ls_residual(a, w, bias, gamma, resid)
+    y_ref = ops.layernorm_fwd(x_ref, ln_w, ln_b, 1e-6)
+    want = torch.nn.functional.layer_norm(x_ref, (N,), ln_w, ln_b, 1e-6)
+    assert rel(y_ref.float(), want) < 4e-3
+    for it in range(6):
+        x = torch.full((M, N), float("nan"), device="cuda")
+        y = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+        ops.gemm_bias_ls_residual_ln(a, w, bias, gamma, resid, ln_w, ln_b, 1e-6, out=x, ln_out=y, one_launch=1)
+        assert torch.equal(x, x_ref), f"residual stream differs (iteration {it})"
+        assert torch.equal(y, y_ref), f"LayerNorm output differs (iteration {it}): {rel(y.float(), y_ref.float()):.3e}"
+
+
 def test_gemm_ls_accumulate_in_place():
     ops = _cuda()
     g = torch.Generator(device="cuda").manual_seed(21)
