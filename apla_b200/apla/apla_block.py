@@ -141,6 +141,14 @@ class FusedAplaBlock(nn.Module):
         self._ms_key = None
 
     # ---- bf16 working copies of the frozen MLP / norm / LayerScale tensors -----------------------------------------
+    def refresh_working_set(self):
+        """Drop the cached copies of this block's frozen MLP / norm / LayerScale tensors and of its attention
+        (`APLA_Attention.refresh_working_set` explains when that is needed)."""
+        self._ms = None
+        self._ms_key = None
+        if hasattr(self.attn, "refresh_working_set"):
+            self.attn.refresh_working_set()
+
     def _mlp_working_set(self, device):
         tk = APLA_Attention._tkey
         g1, g2 = _gamma_of(self.ls1), _gamma_of(self.ls2)

@@ -129,9 +129,22 @@ class APLA_Attention(nn.Module):
     def _tkey(t):
         return (t.data_ptr(), t._version, t.device)
 
+    def refresh_working_set(self):
+        """Drop the cached bf16 working copies; the next forward rebuilds them from the parameters.
+
+        The cache is keyed on (data_ptr, _version, device) of every source tensor, which sees optimiser steps, `copy_`,
+        `load_state_dict` and `.to()`.  It does NOT see a write that bypasses autograd's version counter: `p.data.add_()`,
+        an optimiser that steps on `.data`, or an external kernel writing through the raw pointer.  After such a write
+        call this (or `torch.autograd.graph.increment_version(p)`, which is what `SSLMetaArch.update_teacher` does after
+        its fused EMA kernel)."""
+        self._ws = None
+        self._ws_key = None
+        self._ws_train_key = None
+
     def _working_set(self, device):
         """Dense bf16 copies consumed by the kernels.  Frozen tensors are converted once; the trainable rows are
-        scattered into the dense projection copies again whenever proj_weight1 / proj_bias1 changed."""
+        scattered into the dense projection copies again whenever proj_weight1 / proj_bias1 changed (see
+        `refresh_working_set` for the one kind of write this cannot notice)."""
         frozen_key = (self._tkey(self.qkv.weight), self._tkey(self.proj_weight2), self._tkey(self.proj_bias2),
                       None if self.qkv.bias is None else self._tkey(self.qkv.bias))
         r, D = self.partial_size, self.dim

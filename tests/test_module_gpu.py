@@ -132,3 +132,26 @@ def test_step_is_deterministic():
     for lg, xs, gr in runs[1:]:
         assert torch.equal(lg, runs[0][0]) and torch.equal(xs, runs[0][1])
         assert float((gr - runs[0][2]).norm() / runs[0][2].norm()) < 1e-5
+
+
+def test_refresh_working_set_after_a_write_through_data():
+    """The bf16 working copies are keyed on (data_ptr, _version): an optimiser step or copy_ is noticed, a write through
+    `.data` is not -- `refresh_working_set()` is the documented way to pick it up."""
+    APLA_Attention, _, _, AplaConfig = _mods()
+    mod = _init(APLA_Attention(AplaConfig(8), 128, num_heads=2, qkv_bias=True), seed=4).eval()
+    x = torch.randn(2, 33, 128, device="cuda")
+    with torch.no_grad():
+        y0, _ = mod(x)
+        mod.proj_weight1.add_(0.5)                               # versioned write: seen
+        y1, _ = mod(x)
+        assert rel(y1, y0) > 1e-3
+        mod.proj_weight1.data.add_(0.5)                          # bypasses the version counter: not seen ...
+        y2, _ = mod(x)
+        assert torch.equal(y2, y1)
+        mod.refresh_working_set()                                # ... until asked
+        y3, _ = mod(x)
+        assert rel(y3, y1) > 1e-3
+        mod.qkv.weight.data.mul_(0.5)                            # frozen tensors likewise
+        mod.refresh_working_set()
+        y4, _ = mod(x)
+        assert rel(y4, y3) > 1e-3
