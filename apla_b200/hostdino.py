@@ -279,3 +279,16 @@ class SSLMetaArch(nn.Module):
             from .dinov2 import update_teacher as ema_fn
         for k in self.student.keys():
             ema_fn(list(self.student[k].parameters()), list(self.teacher[k].parameters()), m)
+
+    def cancel_last_layer_grads(self) -> int:
+        """Drop the gradients of the student head's last (weight-normalised prototype) layer: what the reference does after
+        backward while `epoch <= freeze_last_layer_epochs` (`possibly_cancel_last_layer_grads`, dinov2/trainer.py:86-91 ->
+        `cancel_gradients`, utils/_utils.py:416-419: `p.grad = None` for every parameter whose name contains the
+        attribute).  Call between `backward()` and `optimizer.step()`; -> number of tensors whose gradient was dropped."""
+        n = 0
+        for name, p in self.named_parameters():
+            if "student.dino_head.last_layer" in name or "student.ibot_head.last_layer" in name:
+                if p.grad is not None:
+                    n += 1
+                p.grad = None
+        return n

@@ -70,3 +70,57 @@ class WarmupCosineSchedule:
         """Set `engine.lr` for the step about to run (the captured graph reads it from its device-side scalar)."""
         engine.lr = self.lr_at(iteration)
         return engine.lr
+
+
+class CosineSchedule:
+    """The per-iteration schedule of the self-supervised (DINOv2) step: `freeze_iters` zeros, a linear ramp of
+    `warmup_iters` values from `start_warmup_value` to `base_value` INCLUSIVE of both ends (numpy linspace), then a
+    half cosine from `base_value` to `final_value` over the remaining iterations; reads past the end return
+    `final_value`.  Restates `CosineScheduler` (src/self_supervised/dinov2/dinov2_utils.py:143-166) without numpy arrays."""
+
+    def __init__(self, base_value: float, final_value: float, total_iters: int, warmup_iters: int = 0,
+                 start_warmup_value: float = 0.0, freeze_iters: int = 0):
+        self.base_value, self.final_value = float(base_value), float(final_value)
+        self.total_iters, self.warmup_iters, self.freeze_iters = int(total_iters), int(warmup_iters), int(freeze_iters)
+        self.start_warmup_value = float(start_warmup_value)
+        self.zero_until = 0                     # iterations forced to 0 (the frozen last layer, trainer.py:45-47)
+        if self.total_iters < self.warmup_iters + self.freeze_iters:
+            raise ValueError("total_iters is shorter than freeze + warm-up")
+
+    def __getitem__(self, it: int) -> float:
+        if it >= self.total_iters:
+            return self.final_value
+        if it < self.zero_until or it < self.freeze_iters:
+            return 0.0
+        k = it - self.freeze_iters
+        if k < self.warmup_iters:
+            if self.warmup_iters == 1:
+                return self.start_warmup_value
+            return self.start_warmup_value + (self.base_value - self.start_warmup_value) * k / (self.warmup_iters - 1)
+        n = self.total_iters - self.warmup_iters - self.freeze_iters
+        j = k - self.warmup_iters
+        return self.final_value + 0.5 * (self.base_value - self.final_value) * (1.0 + math.cos(math.pi * j / n))
+
+
+def build_ssl_schedules(*, lr: float, lr_eta_min: float, lr_warmup_epochs: int, weight_decay: float, momentum_teacher: float,
+                        final_momentum_teacher: float, warmup_teacher_temp: float, teacher_temp: float,
+                        warmup_teacher_temp_epochs: int, freeze_last_layer_epochs: int, iters_per_epoch: int, epochs: int):
+    """-> dict(lr, wd, momentum, teacher_temp, last_layer_lr) of `CosineSchedule`s, composed as `build_schedulers` does
+    (src/self_supervised/dinov2/trainer.py:7-56): lr warm-up from 0 then cosine to the yml's CosineAnnealingLR.eta_min;
+    weight decay cosine from its base value to the hard-coded 1e-4; teacher momentum cosine to its final value; teacher
+    temperature a linear ramp that then stays; the last layer's rate = lr with its first `freeze_last_layer_epochs`
+    epochs at 0.  Per step (trainer.py:106-140): `lr[k]`, `wd[k]` go to the optimiser, `teacher_temp[k]` into the
+    forward (`SSLMetaArch.forward(..., teacher_temp=)`), `momentum[k]` into `update_teacher`."""
+    total = iters_per_epoch * epochs
+    lr_kw = dict(base_value=lr, final_value=lr_eta_min, total_iters=total, warmup_iters=lr_warmup_epochs * iters_per_epoch,
+                 start_warmup_value=0.0)
+    last = CosineSchedule(**lr_kw)
+    last.zero_until = freeze_last_layer_epochs * iters_per_epoch
+    tt_iters = warmup_teacher_temp_epochs * iters_per_epoch
+    return dict(
+        lr=CosineSchedule(**lr_kw),
+        wd=CosineSchedule(base_value=weight_decay, final_value=1e-4, total_iters=total),
+        momentum=CosineSchedule(base_value=momentum_teacher, final_value=final_momentum_teacher, total_iters=total),
+        teacher_temp=CosineSchedule(base_value=teacher_temp, final_value=teacher_temp, total_iters=tt_iters,
+                                    warmup_iters=tt_iters, start_warmup_value=warmup_teacher_temp),
+        last_layer_lr=last)

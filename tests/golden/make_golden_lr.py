@@ -80,3 +80,41 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# ---- the self-supervised (DINOv2) step: CosineScheduler (src/self_supervised/dinov2/dinov2_utils.py:143-166) --------------
+def ssl_sequences():
+    """The five schedules `build_schedulers` creates (src/self_supervised/dinov2/trainer.py:7-56) with the ISIC2019 values
+    (params/pretrain/dinov2/ISIC2019/vit_b/__common__.yml:135-140,169-195 + apla.yml:12), at a reduced iteration count."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_dinov2_utils", os.path.join(mg.REF, "self_supervised/dinov2/dinov2_utils.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    CS = mod.CosineScheduler
+    ipe, epochs = 7, 12                       # iterations per epoch, epochs (the yml has 300 epochs)
+    total = ipe * epochs
+    cfg = dict(lr=1e-3, eta_min=1e-6, lr_warmup_epochs=2, weight_decay=1e-5, momentum_teacher=0.994, final_momentum_teacher=1.0,
+               warmup_teacher_temp=0.04, teacher_temp=0.07, warmup_teacher_temp_epochs=3, freeze_last_layer_epochs=1,
+               iters_per_epoch=ipe, epochs=epochs)
+    lr = CS(base_value=cfg["lr"], final_value=cfg["eta_min"], total_iters=total, warmup_iters=cfg["lr_warmup_epochs"] * ipe,
+            start_warmup_value=0)
+    wd = CS(base_value=cfg["weight_decay"], final_value=1e-4, total_iters=total, warmup_iters=0)
+    mom = CS(base_value=cfg["momentum_teacher"], final_value=cfg["final_momentum_teacher"], total_iters=total, warmup_iters=0)
+    tt = CS(base_value=cfg["teacher_temp"], final_value=cfg["teacher_temp"], total_iters=cfg["warmup_teacher_temp_epochs"] * ipe,
+            warmup_iters=cfg["warmup_teacher_temp_epochs"] * ipe, start_warmup_value=cfg["warmup_teacher_temp"])
+    last = CS(base_value=cfg["lr"], final_value=cfg["eta_min"], total_iters=total, warmup_iters=cfg["lr_warmup_epochs"] * ipe,
+              start_warmup_value=0)
+    last.schedule[: cfg["freeze_last_layer_epochs"] * ipe] = 0
+    n = total + 3                                # a few reads past the end (-> final_value)
+    return dict(config=cfg, lr=[float(lr[i]) for i in range(n)], wd=[float(wd[i]) for i in range(n)],
+                momentum=[float(mom[i]) for i in range(n)], teacher_temp=[float(tt[i]) for i in range(n)],
+                last_layer_lr=[float(last[i]) for i in range(n)])
+
+
+if __name__ == "__main__":
+    with open(os.path.join(HERE, "lr_schedule.json")) as f:
+        d = json.load(f)
+    d["ssl"] = ssl_sequences()
+    with open(os.path.join(HERE, "lr_schedule.json"), "w") as f:
+        json.dump(d, f)
+    print("ssl", {k: (len(v), v[:2], v[-1]) for k, v in d["ssl"].items() if k != "config"})

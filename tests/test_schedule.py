@@ -46,3 +46,24 @@ def test_from_reference_yaml_mapping_and_apply():
     assert s.apply(e, 3) == e.lr == s.lr_at(3)
     with pytest.raises(NotImplementedError):
         WarmupCosineSchedule.from_reference_config(dict(optimizer=opt["optimizer"], scheduler=dict(type="OneCycleLR", params={})), 10, 1)
+
+
+def test_ssl_schedules_match_reference_cosine_scheduler():
+    """The five schedules of the DINOv2 step against `CosineScheduler` / `build_schedulers` of the reference."""
+    from apla_b200.schedule import build_ssl_schedules
+    with open(os.path.join(HERE, "golden", "lr_schedule.json")) as f:
+        ssl = json.load(f)["ssl"]
+    c = ssl["config"]
+    s = build_ssl_schedules(lr=c["lr"], lr_eta_min=c["eta_min"], lr_warmup_epochs=c["lr_warmup_epochs"],
+                            weight_decay=c["weight_decay"], momentum_teacher=c["momentum_teacher"],
+                            final_momentum_teacher=c["final_momentum_teacher"], warmup_teacher_temp=c["warmup_teacher_temp"],
+                            teacher_temp=c["teacher_temp"], warmup_teacher_temp_epochs=c["warmup_teacher_temp_epochs"],
+                            freeze_last_layer_epochs=c["freeze_last_layer_epochs"], iters_per_epoch=c["iters_per_epoch"],
+                            epochs=c["epochs"])
+    for name in ("lr", "wd", "momentum", "teacher_temp", "last_layer_lr"):
+        want = ssl[name]
+        for k, b in enumerate(want):
+            a = s[name][k]
+            assert abs(a - b) <= 1e-12 + 1e-9 * abs(b), (name, k, a, b)
+    assert s["last_layer_lr"][0] == 0.0 and s["last_layer_lr"][c["iters_per_epoch"]] == s["lr"][c["iters_per_epoch"]]
+    assert s["teacher_temp"][10 ** 6] == c["teacher_temp"]

@@ -494,3 +494,18 @@ def test_meta_arch_sinkhorn_knopp_centering(monkeypatch):
     with pytest.raises(ValueError):
         SSLMetaArch(torch.nn.Identity(), torch.nn.Identity(), torch.nn.Identity(), torch.nn.Identity(), 8,
                     centering="sinkhorn_knopp", fused_objective=True)
+
+
+def test_cancel_last_layer_grads_drops_only_the_student_prototype_layer():
+    """possibly_cancel_last_layer_grads (dinov2/trainer.py:86-91): while the last layer is frozen its gradients are set to
+    None after backward -- the student head's `last_layer.weight_g / weight_v` and nothing else."""
+    import apla_b200.dinov2 as D
+    from apla_b200.hostdino import SSLMetaArch
+    head = lambda: D.DINOHead(16, 32, nlayers=2, hidden_dim=16, bottleneck_dim=8)          # noqa: E731
+    model = SSLMetaArch(torch.nn.Linear(4, 4), torch.nn.Linear(4, 4), head(), head(), 32)
+    for p in model.parameters():
+        p.grad = torch.ones_like(p)
+    dropped = model.cancel_last_layer_grads()
+    names = {n for n, p in model.named_parameters() if p.grad is None}
+    assert dropped == 2 and names == {"student.dino_head.last_layer.weight_g", "student.dino_head.last_layer.weight_v"}
+    assert model.cancel_last_layer_grads() == 0
