@@ -262,3 +262,30 @@ def test_engine_vs_live_oracle_shapes(dim, heads, depth, r, batch, img, layersca
     theirs = torch.cat([ref.grads[k].flatten() for k in eng.trainable_names()])
     assert cosine(ours, theirs) >= 0.999, cosine(ours, theirs)
     assert rel(ours, theirs) <= 1e-2, rel(ours, theirs)
+
+
+@pytest.mark.parametrize("r", [16, 128])
+def test_side_stream_weight_gradient_matches(monkeypatch, r):
+    """APLA_SIDE_WGRAD=1 runs every block's weight / bias gradient on the engine's side stream (fork / join events, also
+    inside the captured graph; r == dim reads dxb, r < dim alternates two dsub slots): same gradients, same trajectory."""
+    from apla_b200.config import AplaConfig
+    from apla_b200.hostvit import VitArch, build_classifier
+    res = {}
+    for side in ("0", "1"):
+        monkeypatch.setenv("APLA_SIDE_WGRAD", side)
+        model = build_classifier(VitArch(128, 4, 2), img_size=56, patch_size=14, n_classes=10, apla_config=AplaConfig(r), seed=0)
+        eng = _engine(model, 6, 56)
+        assert eng.side_wgrad == (side == "1")
+        g = torch.Generator().manual_seed(12)
+        images = torch.randn(6, 3, 56, 56, generator=g).cuda()
+        labels = torch.randint(0, 10, (6,), generator=g).cuda()
+        eng.forward(images, labels)
+        eng.backward()
+        torch.cuda.synchronize()
+        g0 = eng.grads.clone()
+        for _ in range(4):                                     # eager, captured, replayed
+            eng.step(images, labels)
+        torch.cuda.synchronize()
+        res[side] = (g0, eng.params.clone())
+    assert rel(res["1"][0], res["0"][0]) < 1e-5
+    assert rel(res["1"][1], res["0"][1]) < 1e-5
