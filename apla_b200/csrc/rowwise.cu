@@ -4,6 +4,8 @@
 // Reference ops replaced: nn.LayerNorm(eps=1e-6) src/utils/transformers/vit.py:519,536,554,571 and :280,:285;
 // LayerScale backward vit.py:243-244; scatter_ backward (= gather) src/apla/appla_attn.py:70-79;
 // PatchEmbed / cls / pos add vit.py:304-307, :389-396.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -263,6 +265,59 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ a, int64_t ld, i
   }
 }
 
+// The same for a WIDE matrix (partial_size == dim: n = 768 / 1024 columns of the dense dY): 16-byte loads, a warp covers 256
+// consecutive columns of a row (512 contiguous bytes), 8 warps x `rows_per_block / 8` rows each with four loads in flight,
+// one fp32 atomic per column and block.  (The narrow kernel above reads 2 bytes per thread: 1.5 TB/s on this shape.)
+__global__ void __launch_bounds__(256)
+colsum_wide_kernel(const __nv_bfloat16* __restrict__ a, int64_t ld, int rows, int n, float* __restrict__ out,
+                   const int* __restrict__ rowmap, int rows_per_block) {
+  __shared__ float red[8][256 + 8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col0 = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col0 < n) {
+    const __nv_bfloat16* base = a + col0;
+    int r = r0 + w;
+    for (; r + 24 < r1; r += 32) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const uint4*>(base + int64_t(r + 8 * u) * ld));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t q[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          acc[2 * t] += bf16_lo(q[t]);
+          acc[2 * t + 1] += bf16_hi(q[t]);
+        }
+      }
+    }
+    for (; r < r1; r += 8) {
+      const uint4 v = __ldcs(reinterpret_cast<const uint4*>(base + int64_t(r) * ld));
+      const uint32_t q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        acc[2 * t] += bf16_lo(q[t]);
+        acc[2 * t + 1] += bf16_hi(q[t]);
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) red[w][lane * 8 + t] = acc[t];
+  __syncthreads();
+  const int c = threadIdx.x;                       // one column of the block's 256 per thread
+  const int col = blockIdx.x * 256 + c;
+  if (col < n) {
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += red[k][c];
+    const int o = rowmap ? rowmap[col] : col;
+    if (o >= 0) atomicAdd(out + o, sum);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // patch extraction: images fp32 [B,3,S,S] -> bf16 [B*P, kpad], k = (c, py, px)  (conv k=s=p as a GEMM)
 // ------------------------------------------------------------------------------------------------
@@ -406,6 +461,18 @@ int ls_cast(const float* x, int64_t ldx, const float* gamma, void* out, int64_t 
 
 int colsum(const void* a, int64_t ld, int rows, int n, float* out, const int* rowmap, cudaStream_t stream) {
   APLA_CHECK(rows > 0 && n > 0, "colsum: empty");
+  static const bool narrow_only = [] { const char* e = getenv("APLA_COLSUM_NARROW"); return e && atoi(e) != 0; }();   // A/B switch
+  if (!narrow_only && n >= 256 && n % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+    // enough row slices to put ~8 blocks on every SM, at least 32 rows (4 per warp) each
+    const int col_blocks = cdiv(n, 256);
+    int rpb = cdiv(rows, cdiv(sm_count() * 8, col_blocks));
+    rpb = rpb < 32 ? 32 : (rpb + 7) / 8 * 8;
+    dim3 grid(col_blocks, cdiv(rows, rpb));
+    colsum_wide_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a), ld, rows, n, out, rowmap, rpb);
+    APLA_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+  }
   const int rows_per_block = 64;
   dim3 grid(cdiv(n, 32), cdiv(rows, rows_per_block));
   colsum_kernel<<<grid, dim3(32, 8), 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a), ld, rows, n, out, rowmap,

@@ -218,6 +218,30 @@ def test_proj_wgrad_full_rowmap():
     assert rel(db, dy[:, perm].float().sum(0)) < 1e-3
 
 
+@pytest.mark.parametrize("T,n,ld", [(16448, 768, 768), (58496, 1024, 1024), (1031, 768, 768), (7, 256, 256), (515, 264, 272),
+                                    (300, 64, 64)])
+def test_colsum_wide_and_narrow(T, n, ld):
+    """Bias gradient = column sums of a bf16 matrix, scattered through rowmap (entries < 0 are dropped): the 16-byte-load
+    kernel for wide matrices (n >= 256) and the narrow one, incl. a padded leading dimension and ragged row counts."""
+    ops = _cuda()
+    g = torch.Generator(device="cuda").manual_seed(T + n)
+    full = bf(torch.randn(T, ld, device="cuda", generator=g))
+    dy = full[:, :n]
+    perm = torch.randperm(n, device="cuda", generator=g)
+    rowmap = torch.empty(n, dtype=torch.int32, device="cuda")
+    rowmap[perm] = torch.arange(n, dtype=torch.int32, device="cuda")
+    rowmap[perm[: n // 5]] = -1                                           # a fifth of the columns has no slot
+    db = torch.zeros(n, device="cuda")
+    ops.colsum(dy, db, n, rowmap=rowmap)
+    ref = torch.zeros(n, device="cuda")
+    keep = rowmap >= 0
+    ref[rowmap[keep].long()] = dy.float().sum(0)[keep]
+    assert rel(db, ref) < 1e-4, rel(db, ref)
+    db2 = torch.zeros(n, device="cuda")
+    ops.colsum(dy, db2, n)
+    assert rel(db2, dy.float().sum(0)) < 1e-4
+
+
 @pytest.mark.parametrize("D", [128, 384, 768, 1024])
 def test_layernorm_fwd_bwd(D):
     ops = _cuda()
