@@ -204,14 +204,20 @@ def koleo_bwd(x, xn, nn, dist, eps: float, gscale: Optional[torch.Tensor], group
     return dx
 
 
-def ema_update_(teacher: torch.Tensor, student: torch.Tensor, m: float) -> torch.Tensor:
-    """teacher <- m * teacher + (1 - m) * student, in place (f32, contiguous, same number of elements)."""
+def ema_check(teacher: torch.Tensor, student: torch.Tensor) -> None:
+    """The argument checks of `ema_update_` alone (a pair the caller skips must still be one the kernel would accept:
+    no silent CPU path)."""
     require_device()
     for t, name in ((teacher, "teacher"), (student, "student")):
         if not t.is_cuda or t.dtype != F32 or not t.is_contiguous():
             raise RuntimeError(f"{name} must be a contiguous f32 CUDA tensor")
     if teacher.numel() != student.numel():
         raise RuntimeError("teacher and student differ in size")
+
+
+def ema_update_(teacher: torch.Tensor, student: torch.Tensor, m: float) -> torch.Tensor:
+    """teacher <- m * teacher + (1 - m) * student, in place (f32, contiguous, same number of elements)."""
+    ema_check(teacher, student)
     LIB.call("apla_ema_update", ptr(teacher), ptr(student), teacher.numel(), float(m), stream())
     return teacher
 

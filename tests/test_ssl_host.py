@@ -509,3 +509,30 @@ def test_cancel_last_layer_grads_drops_only_the_student_prototype_layer():
     names = {n for n, p in model.named_parameters() if p.grad is None}
     assert dropped == 2 and names == {"student.dino_head.last_layer.weight_g", "student.dino_head.last_layer.weight_v"}
     assert model.cancel_last_layer_grads() == 0
+
+
+def test_update_teacher_skips_frozen_identical_pairs(monkeypatch):
+    """Frozen student tensors that the teacher holds bit-identically are left alone (no launch, no version bump -> the
+    teacher's cached weight copies / position table stay valid); trainable pairs and frozen-but-different pairs are averaged."""
+    from apla_b200.dinov2 import loss
+    calls = []
+
+    class CountingOps:
+        @staticmethod
+        def ema_update_(t, s, m):
+            calls.append(t.data_ptr())
+            t.mul_(m).add_(s, alpha=1 - m)
+            return t
+    monkeypatch.setattr(loss, "ops", CountingOps)
+    s_frozen, s_train, s_frozen2 = torch.randn(8), torch.randn(8, requires_grad=True), torch.randn(8)
+    t_same, t_train, t_diff = s_frozen.clone(), s_train.detach().clone() + 1.0, s_frozen2.clone() + 1.0
+    v_same = t_same._version
+    for _ in range(3):
+        loss.update_teacher([s_frozen, s_train, s_frozen2], [t_same, t_train, t_diff], 0.5)
+    assert calls.count(t_same.data_ptr()) == 0 and t_same._version == v_same and torch.equal(t_same, s_frozen)
+    assert calls.count(t_train.data_ptr()) == 3 and calls.count(t_diff.data_ptr()) == 3
+    assert torch.allclose(t_diff, s_frozen2 + 0.125) and torch.allclose(t_train, s_train.detach() + 0.125)
+    with torch.no_grad():
+        s_frozen.add_(1.0)                               # the frozen student tensor changed after all: averaged again
+    loss.update_teacher([s_frozen], [t_same], 0.5)
+    assert calls.count(t_same.data_ptr()) == 1 and torch.allclose(t_same, s_frozen - 0.5)
