@@ -19,6 +19,7 @@ Tested against oracle/ssl_oracle.py (itself pinned to the reference) in tests/te
 """
 from __future__ import annotations
 
+import weakref
 from typing import List, Optional, Sequence
 
 import torch
@@ -256,22 +257,25 @@ class KoLeoLoss(nn.Module):
         return _KoLeo.apply(student_output.contiguous(), eps, chunks)
 
 
+# id(student tensor) -> (weak references to that tensor and to its teacher twin, both versions at the time of the check,
+# verdict).  Validated through the OBJECTS, not through addresses: the caching allocator hands the addresses of a freed
+# model to the next one.  (Not a WeakKeyDictionary: it compares keys with ==, which is element-wise for tensors.)
 _FROZEN_PAIR_IS_IDENTICAL = {}
 
 
 def _frozen_and_identical(s: torch.Tensor, t: torch.Tensor) -> bool:
     """A student parameter that does not train never changes; if the teacher's copy holds the same values (it is loaded
     from the student, models.py:138), `m * t + (1 - m) * s` leaves it where it is, up to the rounding of that expression.
-    Checked once per (student tensor, teacher tensor, versions) pair."""
+    Checked once per (student tensor, teacher tensor) pair and again whenever either version moved."""
     if s.requires_grad or s.shape != t.shape:
         return False
-    key = (s.data_ptr(), t.data_ptr(), s._version, t._version, s.numel(), str(s.device))
-    same = _FROZEN_PAIR_IS_IDENTICAL.get(key)
-    if same is None:
-        same = bool(torch.equal(s.data, t.data))
-        if len(_FROZEN_PAIR_IS_IDENTICAL) > 8192:
-            _FROZEN_PAIR_IS_IDENTICAL.clear()
-        _FROZEN_PAIR_IS_IDENTICAL[key] = same
+    key = id(s)
+    hit = _FROZEN_PAIR_IS_IDENTICAL.get(key)
+    if hit is not None and hit[0]() is s and hit[1]() is t and hit[2] == s._version and hit[3] == t._version:
+        return hit[4]
+    same = bool(torch.equal(s.data, t.data))
+    _FROZEN_PAIR_IS_IDENTICAL[key] = (weakref.ref(s, lambda _, k=key: _FROZEN_PAIR_IS_IDENTICAL.pop(k, None)),
+                                      weakref.ref(t), s._version, t._version, same)
     return same
 
 
