@@ -28,6 +28,8 @@ output has the input's dtype.  CUDA (sm_100a) only, no fallback; dropout / drop-
 from __future__ import annotations
 
 import ctypes
+import os
+import weakref
 from typing import List, Optional, Sequence
 
 import torch
@@ -35,6 +37,9 @@ import torch.nn as nn
 
 from .._lib import LIB, BlockWeights, ptr, require_device, stream
 from .appla_attn import APLA_Attention, _pad64
+
+
+_CHAIN = os.environ.get("APLA_BLOCK_CHAIN", "1") != "0"      # hand bf16(gamma2 * dx) from block to block in backward
 
 
 class _AplaBlockFn(torch.autograd.Function):
@@ -64,6 +69,7 @@ class _AplaBlockFn(torch.autograd.Function):
         LIB.call("apla_block_fwd", ctypes.addressof(nat), ptr(x_in), ptr(x_mid), ptr(x_out), ptr(ln_tmp), ptr(qkv), ptr(ao),
                  ptr(lse), ptr(dgelu), ptr(gelu_tmp), ptr(cu_seqlens), num_seqs, max_len, T, stream())
         ctx.blk, ctx.nat, ctx.refs = blk, nat, blk._nat_refs      # the struct points into these tensors
+        blk._dyb_stash = None                                     # (see backward: nothing survives from the last step)
         ctx.geom = (num_seqs, max_len, cu_seqlens)
         ctx.x_dtype, ctx.x_shape = x.dtype, x.shape
         ctx.save_for_backward(x_in, x_mid, qkv, ao, lse, dgelu)
@@ -82,7 +88,19 @@ class _AplaBlockFn(torch.autograd.Function):
         T = dx_out.shape[0]
         dev, bf, f32 = dy.device, torch.bfloat16, torch.float32
         dx_mid = torch.empty(T, D, device=dev, dtype=f32)        # the input gradient lands in the same buffer
-        dyb = torch.empty(T, D, device=dev, dtype=bf)
+        # Chained blocks (fuse_apla_blocks links each fused block to the one in front of it): the first thing a block's
+        # backward needs is bf16(gamma2 * dy), a 6-byte-per-element pass over the gradient the block behind it has just
+        # written.  That block writes it from its last LayerNorm backward instead and leaves it here -- accepted only if
+        # `dy` IS that gradient, untouched: same storage, same version counter (autograd accumulating a second consumer's
+        # gradient into it, in place or not, changes one of the two).
+        stash, blk._dyb_stash = getattr(blk, "_dyb_stash", None), None
+        dyb_ready = int(stash is not None and stash[0] == dx_out.data_ptr() and stash[1] == dx_out._version
+                        and stash[2] == T and stash[3].device == dev)
+        dyb = stash[3] if dyb_ready else torch.empty(T, D, device=dev, dtype=bf)
+        front = blk._front_ref() if getattr(blk, "_front_ref", None) is not None else None
+        chain = bool(want_x and front is not None and _CHAIN and front.attn.dim == D)
+        dyb_front = torch.empty(T, D, device=dev, dtype=bf) if chain else None
+        g_front = front._mlp_working_set(dev)["g2"] if chain else None
         dh = torch.empty(T, Hd, device=dev, dtype=bf)
         dln = torch.empty(T, D, device=dev, dtype=bf)
         dsub = torch.empty(T, nat.r_pad, device=dev, dtype=bf) if (want_w and not nat.rowmap) else None
@@ -96,8 +114,11 @@ class _AplaBlockFn(torch.autograd.Function):
             db1 = torch.empty(r, device=dev, dtype=f32)
         LIB.call("apla_block_bwd", ctypes.addressof(nat), ptr(dx_out), ptr(x_in), ptr(x_mid), ptr(qkv), ptr(ao), ptr(lse),
                  ptr(dgelu), ptr(dx_mid), ptr(dx_mid) if want_x else None, ptr(dyb), ptr(dh), ptr(dln), ptr(dsub), ptr(d_ao),
-                 ptr(delta), ptr(dqkv), ptr(dw1), ptr(db1), ptr(cu), num_seqs, max_len, T, stream())
+                 ptr(delta), ptr(dqkv), ptr(dw1), ptr(db1), ptr(cu), num_seqs, max_len, T, dyb_ready, ptr(dyb_front),
+                 ptr(g_front), stream())
         dx = dx_mid.view(ctx.x_shape).to(ctx.x_dtype) if want_x else None
+        if chain and dx.data_ptr() == dx_mid.data_ptr():
+            front._dyb_stash = (dx_mid.data_ptr(), dx._version, T, dyb_front)
         return dx, dw1, db1, None, None, None
 
 
@@ -284,6 +305,15 @@ def fuse_apla_blocks(model: nn.Module) -> nn.Module:
         if isinstance(getattr(blk, "attn", None), APLA_Attention):
             bb.blocks[i] = FusedAplaBlock(blk)
             n += 1
+    # each fused block learns which fused block is in front of it (a weak reference outside the module tree: state-dict
+    # keys and `.modules()` stay as they were); see _AplaBlockFn.backward
+    prev = None
+    for blk in bb.blocks:
+        if isinstance(blk, FusedAplaBlock):
+            object.__setattr__(blk, "_front_ref", weakref.ref(prev) if prev is not None else None)
+            prev = blk
+        else:
+            prev = None
     if n == 0 and not any(isinstance(b, FusedAplaBlock) for b in bb.blocks):
         raise RuntimeError("no block carries an APLA_Attention: call build_apla(config, model, attn_class) first "
                            "(multi-GPU partial_size='full' keeps the stock attention and cannot be fused)")

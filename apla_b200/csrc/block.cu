@@ -50,7 +50,8 @@ int apla_block_fwd(const apla_block_weights* w, const float* x_in, float* x_mid,
 int apla_block_bwd(const apla_block_weights* w, const float* dx_out, const float* x_in, const float* x_mid,
                    const void* qkv, const void* ao, const float* lse, const void* dgelu, float* dx_mid, float* dx_in,
                    void* dyb, void* dh, void* dln, void* dsub, void* d_ao, float* delta, void* dqkv, float* dw1,
-                   float* db1, const int32_t* cu_seqlens, int num_seqs, int max_seqlen, int T, apla_stream_t stream) {
+                   float* db1, const int32_t* cu_seqlens, int num_seqs, int max_seqlen, int T, int dyb_ready,
+                   void* dyb_prev, const float* gamma_prev, apla_stream_t stream) {
   if (int rc = check_weights(w, "apla_block_bwd")) return rc;
   APLA_CHECK(T > 0 && num_seqs > 0 && max_seqlen > 0, "apla_block_bwd: empty problem");
   APLA_CHECK(dx_out && x_mid && dgelu && dx_mid && dyb && dh && dln && w->wfc1T && w->wfc2T, "apla_block_bwd: null buffer");
@@ -62,7 +63,10 @@ int apla_block_bwd(const apla_block_weights* w, const float* dx_out, const float
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int D = w->D, Hd = w->hidden, r = w->r;
   // MLP branch: dyb = bf16(gamma2 * dx_out) -> fc2 dgrad x gelu' -> fc1 dgrad
-  if (int rc = ls_cast(dx_out, D, w->g2, dyb, D, T, D, s)) return rc;
+  // (dyb_ready: the block behind this one already wrote it from its LayerNorm-1 backward, see the header)
+  if (!dyb_ready) {
+    if (int rc = ls_cast(dx_out, D, w->g2, dyb, D, T, D, s)) return rc;
+  }
   if (int rc = gemm_tn(EPI_MUL_F16, dyb, w->wfc2T, T, Hd, D, D, D, dh, nullptr, nullptr, nullptr, dgelu, Hd, s, 0)) return rc;
   if (int rc = gemm_tn(EPI_BIAS, dh, w->wfc1T, T, D, Hd, Hd, Hd, dln, nullptr, nullptr, nullptr, nullptr, D, s, 0)) return rc;
   // dx_mid = dx_out + LN2'(dln); dyb = bf16(gamma1 * dx_mid) = gradient at the projection output (+ its APLA columns)
@@ -88,8 +92,9 @@ int apla_block_bwd(const apla_block_weights* w, const float* dx_out, const float
     return rc;
   if (int rc = gemm_tn(EPI_BIAS, dqkv, w->wqkvT, T, D, 3 * D, 3 * D, 3 * D, dln, nullptr, nullptr, nullptr, nullptr, D, s, 0))
     return rc;
-  return layernorm_bwd(dln, D, x_in, D, w->ln1w, dx_mid, D, dx_in, D, nullptr, 0, nullptr, nullptr, 0, nullptr, 0, 0, T, D,
-                       w->eps1, s);
+  // dx_in = dx_mid + LN1'(dln); optionally also bf16(gamma_prev * dx_in) for the block in front
+  return layernorm_bwd(dln, D, x_in, D, w->ln1w, dx_mid, D, dx_in, D, dyb_prev, dyb_prev ? D : 0, dyb_prev ? gamma_prev : nullptr,
+                       nullptr, 0, nullptr, 0, 0, T, D, w->eps1, s);
 }
 
 }  // extern "C"

@@ -274,11 +274,16 @@ int apla_block_fwd(const apla_block_weights* w, const float* x_in, float* x_mid,
                    int max_seqlen, int T, apla_stream_t stream);
 /* dx_out f32[T,D] -> dx_in f32[T,D] (NULL: no input gradient wanted; may alias dx_mid) and dw1 f32[r,D] / db1 f32[r]
  * (NULL: no weight gradient; zeroed here).  dx_mid f32[T,D], dyb bf16[T,D], dh bf16[T,hidden], dln bf16[T,D],
- * dsub bf16[T,r_pad] (compact path), d_ao bf16[T,D], delta f32[T,H], dqkv bf16[T,3D] are scratch. */
+ * dsub bf16[T,r_pad] (compact path), d_ao bf16[T,D], delta f32[T,H], dqkv bf16[T,3D] are scratch.
+ * Chaining consecutive blocks: a block's backward starts by forming dyb = bf16(g2 * dx_out), a pass over the fp32
+ * gradient the block BEHIND it has just written.  That block can write it instead, from the LayerNorm-1 backward that
+ * produces dx_in: give it dyb_prev bf16[T,D] and gamma_prev = the g2 of the block in front (NULL = 1); the block in front
+ * is then called with dyb_ready = 1 and that buffer as dyb.  dyb_prev NULL / dyb_ready 0: the stand-alone behaviour. */
 int apla_block_bwd(const apla_block_weights* w, const float* dx_out, const float* x_in, const float* x_mid,
                    const void* qkv, const void* ao, const float* lse, const void* dgelu, float* dx_mid, float* dx_in,
                    void* dyb, void* dh, void* dln, void* dsub, void* d_ao, float* delta, void* dqkv, float* dw1,
-                   float* db1, const int32_t* cu_seqlens, int num_seqs, int max_seqlen, int T, apla_stream_t stream);
+                   float* db1, const int32_t* cu_seqlens, int num_seqs, int max_seqlen, int T, int dyb_ready,
+                   void* dyb_prev, const float* gamma_prev, apla_stream_t stream);
 
 /* --- step engine: the whole fine-tune step as one native call sequence ------------------------------------ */
 /* Replaces Trainer.global_step's device work (src/defaults/trainer.py:106-138): Classifier.forward

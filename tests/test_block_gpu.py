@@ -224,3 +224,65 @@ def test_fused_block_refuses_what_it_does_not_implement():
         fuse_apla_blocks(stock)
     with pytest.raises(TypeError):
         FusedAplaBlock(stock.backbone.blocks[0])
+
+
+def _chain_case(chain, extra_consumer, packed):
+    """Three fused blocks in a row; gradients of the input and of every trainable row, with / without the block-to-block
+    hand-over of bf16(gamma2 * dx), optionally with a SECOND consumer of an intermediate output (its gradient is then a sum
+    autograd forms, which the hand-over must not be used for)."""
+    import apla_b200.apla.apla_block as AB
+    from apla_b200._lib import LIB
+    from apla_b200.apla import fuse_apla_blocks
+    from apla_b200.config import AplaConfig
+    from apla_b200.hostvit import VitArch, build_classifier
+    from helpers import perturb_module
+    AB._CHAIN = chain
+    model = build_classifier(VitArch(128, 3, 2), img_size=56, patch_size=14, n_classes=10, apla_config=AplaConfig(16), seed=0)
+    perturb_module(model)                                        # LayerScale vectors away from 1, biases away from 0
+    fuse_apla_blocks(model.cuda())
+    blocks = list(model.backbone.blocks)
+    D = model.backbone.embed_dim
+    g = torch.Generator().manual_seed(5)
+    if packed:
+        xs = [torch.randn(2, 257, D, generator=g).cuda().requires_grad_(True), torch.randn(4, 50, D, generator=g).cuda().requires_grad_(True)]
+        h, mids = xs, []
+        for b in blocks:
+            h = b(h)
+            mids.append(h)
+        loss = sum((t.float() ** 2).sum() for t in h)
+        if extra_consumer:
+            loss = loss + (mids[0][0].float() * 0.37).sum()
+        leaves = xs
+    else:
+        x = torch.randn(3, 65, D, generator=g).cuda().requires_grad_(True)
+        h, mids = x, []
+        for b in blocks:
+            h = b(h)
+            mids.append(h)
+        loss = (h.float() ** 2).sum()
+        if extra_consumer:
+            loss = loss + (mids[1].float() * 0.37).sum()
+        leaves = [x]
+    n0 = LIB.load().apla_launch_count()
+    loss.backward()
+    torch.cuda.synchronize()
+    launches = int(LIB.load().apla_launch_count() - n0)
+    grads = [t.grad.clone() for t in leaves]
+    for b in blocks:
+        grads += [b.attn.proj_weight1.grad.clone(), b.attn.proj_bias1.grad.clone()]
+    AB._CHAIN = True
+    return grads, launches, len(blocks)
+
+
+@pytest.mark.parametrize("packed", [False, True])
+@pytest.mark.parametrize("extra_consumer", [False, True])
+def test_gradient_hand_over_between_fused_blocks(packed, extra_consumer):
+    _need_gpu()
+    ref, l_ref, n = _chain_case(False, extra_consumer, packed)
+    got, l_got, _ = _chain_case(True, extra_consumer, packed)
+    for a, b in zip(got, ref):
+        assert rel(a, b) < 1e-5, rel(a, b)                      # (weight gradients: fp32 atomics of the split-K kernel)
+    assert torch.equal(got[0], ref[0])                           # input gradient: same kernels, same operands
+    # every hand-over replaces one launch (the cast) of the block in front; the second consumer blocks it for one block
+    saved = l_ref - l_got
+    assert saved == (n - 1) - (1 if extra_consumer else 0), (l_ref, l_got)
