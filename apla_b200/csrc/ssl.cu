@@ -733,7 +733,9 @@ int ssl_weightnorm_bwd(const float* g, const float* v, const float* dW, int64_t 
 
 int ssl_koleo_fwd(const float* xn, int groups, int n, int D, float eps, float w, int* nn, float* dist, float* row_loss,
                   cudaStream_t s) {
-  APLA_CHECK(groups >= 1 && n >= 2 && D > 0, "koleo_fwd: groups=%d n=%d D=%d (needs at least 2 rows)", groups, n, D);
+  // (n == 1, one image per process: the only candidate is the row itself, as in the reference -- argmax over a diagonal filled
+  //  with -1 -- and the loss is the constant -log(1e-8 sqrt(D) + eps) with a zero gradient)
+  APLA_CHECK(groups >= 1 && n >= 1 && D > 0, "koleo_fwd: groups=%d n=%d D=%d", groups, n, D);
   const size_t smem = size_t(D + 33 + 64) * sizeof(float);
   APLA_CHECK(smem <= 48 * 1024, "koleo_fwd: D=%d too wide for the row buffer", D);
   koleo_nn_kernel<<<dim3(n, groups), 256, smem, s>>>(xn, n, D, eps, w, nn, dist, row_loss);
@@ -744,7 +746,7 @@ int ssl_koleo_fwd(const float* xn, int groups, int n, int D, float eps, float w,
 
 int ssl_koleo_bwd(const float* x, const float* xn, int groups, int n, int D, float eps, float norm_eps, float w,
                   const int* nn, const float* dist, const float* gscale, float* dx, cudaStream_t s) {
-  APLA_CHECK(groups >= 1 && n >= 2 && D > 0, "koleo_bwd: groups=%d n=%d D=%d", groups, n, D);
+  APLA_CHECK(groups >= 1 && n >= 1 && D > 0, "koleo_bwd: groups=%d n=%d D=%d", groups, n, D);
   const size_t smem = size_t(D + 33) * sizeof(float);
   APLA_CHECK(smem <= 48 * 1024, "koleo_bwd: D=%d too wide for the row buffer", D);
   koleo_bwd_kernel<<<dim3(n, groups), 256, smem, s>>>(x, xn, n, D, eps, norm_eps, w, nn, dist, gscale, dx);
