@@ -520,10 +520,13 @@ koleo_bwd_kernel(const float* __restrict__ x, const float* __restrict__ xn, int 
     const float di = db[i];
     const float ci = up / ((di + eps) * di);
     const float* xj = xb + int64_t(nnb[i]) * D;
-    for (int k = threadIdx.x; k < D; k += blockDim.x) gi[k] = ci * (xi[k] - xj[k] + 1e-8f);
+    // a row that is its own neighbour (a group of one row): its two terms cancel exactly -- written out, not left to
+    // c * u - c * u, which a fused multiply-add turns into the rounding error of the first product
+    const bool self = nnb[i] == i;
+    for (int k = threadIdx.x; k < D; k += blockDim.x) gi[k] = self ? 0.f : ci * (xi[k] - xj[k] + 1e-8f);
   }
   for (int j = 0; j < n; ++j) {
-    if (nnb[j] != i) continue;  // uniform over the block
+    if (nnb[j] != i || j == i) continue;  // uniform over the block
     const float dj = db[j];
     const float cj = up / ((dj + eps) * dj);
     const float* xj = xb + int64_t(j) * D;
