@@ -426,8 +426,8 @@ def test_c_abi_argument_checks_without_a_gpu():
         "apla_l2norm_bwd": (None, 0, 1, None, 0, 1, 1, 0, 1e-12, None, 0, None),
         "apla_weightnorm_fwd": (None, None, 0, 4, None, None, None),
         "apla_weightnorm_bwd": (None, None, None, 0, 0, 4, None, None, None),
-        "apla_koleo_fwd": (None, 1, 1, 8, 1e-8, 1.0, None, None, None, None),                   # n < 2
-        "apla_koleo_bwd": (None, None, 1, 1, 8, 1e-8, 1e-8, 1.0, None, None, None, None, None),
+        "apla_koleo_fwd": (None, 1, 0, 8, 1e-8, 1.0, None, None, None, None),                   # n < 1
+        "apla_koleo_bwd": (None, None, 1, 0, 8, 1e-8, 1e-8, 1.0, None, None, None, None, None),
         "apla_ema_update": (None, None, -1, 0.99, None),
         "apla_ssl_objective": (None, 0, None, 0, None, 0, None, None, None, 0, 8, 0, 64, 0.05, 0.1, 1.0, 1.0, None, None, 1,
                                None, 0, 1, None, None, None, None, None),                         # B = 0
