@@ -100,6 +100,8 @@ def main():
     measure("attention backward", lambda i: ops.attn_bwd(qkv[i % R], ob, xs[i % R], lse, H, 0.125, B, N, dqkv=dqkv, delta=delta), 10,
             10.0 * N * D * T)
     measure("layernorm forward", lambda i: ops.layernorm_fwd(xf[i % R], gam, bd, 1e-6, out=ob), 25, mbytes=T * D * 6 / 1e6)
+    measure("ls_cast (fp32 -> bf16, same bytes as layernorm forward, no reductions)", lambda i: ops.ls_cast(xf[i % R], gam, out=ob), 0,
+            mbytes=T * D * 6 / 1e6)
     dres = torch.randn(T, D, device=dev); dxb = torch.empty(T, D, device=dev, dtype=torch.bfloat16)
     measure("layernorm backward", lambda i: ops.layernorm_bwd(xs[i % R], xf[i % R], gam, 1e-6, dres=dres, dx=dres, dxb=dxb), 24,
             mbytes=T * D * 16 / 1e6)
